@@ -1,0 +1,284 @@
+// kernels_generic.cu — the table-driven SIMT tile kernel: every pairwise step, every dtype.
+//
+// Replaces the arithmetic of Muscle.binary_einsum (call sites: /root/reference/src/Operations/overlap.jl:42,46,
+// src/Algorithms/DMRG.jl:17, canonize.jl:44,61, absorb.jl:31 ...): the reference permutes both operands,
+// reshapes and calls BLAS gemm; here operands are gathered straight from their original strides through
+// the additive offset tables (tnb_internal.h), multiplied in a 64x64x8 shared-memory tile with a 4x4
+// register micro-tile per thread, and scattered into the layout the consumer wants.  It is the
+// always-correct path (any rank, strides, batch modes, conj flags, rank-0 operands, alpha/beta) and the
+// one the specialised kernels are checked against.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tnb_internal.h"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, BK = 8, NTHREADS = 256;
+constexpr int PAD = 4;
+
+template <typename R, bool CPLX> struct ElemT;
+template <> struct ElemT<float, true> { typedef float2 type; };
+template <> struct ElemT<double, true> { typedef double2 type; };
+template <> struct ElemT<float, false> { typedef float type; };
+template <> struct ElemT<double, false> { typedef double type; };
+
+__device__ __forceinline__ float2 ezero(float2*) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ double2 ezero(double2*) { return make_double2(0., 0.); }
+__device__ __forceinline__ float ezero(float*) { return 0.f; }
+__device__ __forceinline__ double ezero(double*) { return 0.; }
+
+__device__ __forceinline__ float2 econj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ double2 econj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ float econj(float a) { return a; }
+__device__ __forceinline__ double econj(double a) { return a; }
+
+__device__ __forceinline__ void emac(float2& c, float2 a, float2 b) {
+    c.x = fmaf(a.x, b.x, c.x); c.x = fmaf(-a.y, b.y, c.x);
+    c.y = fmaf(a.x, b.y, c.y); c.y = fmaf(a.y, b.x, c.y);
+}
+__device__ __forceinline__ void emac(double2& c, double2 a, double2 b) {
+    c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+}
+__device__ __forceinline__ void emac(float& c, float a, float b) { c = fmaf(a, b, c); }
+__device__ __forceinline__ void emac(double& c, double a, double b) { c = fma(a, b, c); }
+
+__device__ __forceinline__ float2 eadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 eadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float eadd(float a, float b) { return a + b; }
+__device__ __forceinline__ double eadd(double a, double b) { return a + b; }
+
+// scalar (alpha/beta given as double[2]) times element
+__device__ __forceinline__ float2 escale(const double* s, float2 a) {
+    float sr = (float)s[0], si = (float)s[1];
+    return make_float2(sr * a.x - si * a.y, sr * a.y + si * a.x);
+}
+__device__ __forceinline__ double2 escale(const double* s, double2 a) {
+    return make_double2(s[0] * a.x - s[1] * a.y, s[0] * a.y + s[1] * a.x);
+}
+__device__ __forceinline__ float escale(const double* s, float a) { return (float)s[0] * a; }
+__device__ __forceinline__ double escale(const double* s, double a) { return s[0] * a; }
+
+__device__ __forceinline__ int64_t tab(const TabRef& t, uint32_t i) {
+    uint32_t q = i / t.lo_size;
+    uint32_t r = i - q * t.lo_size;
+    return t.hi[q] + t.lo[r];
+}
+
+template <typename E>
+__device__ __forceinline__ void store_out(E* c, E acc, const double* alpha, const double* beta, bool has_beta) {
+    E v = escale(alpha, acc);
+    if (has_beta) v = eadd(v, escale(beta, *c));
+    *c = v;
+}
+
+template <typename R, bool CPLX>
+__global__ void __launch_bounds__(NTHREADS) einsum_tile_kernel(const EinsumArgs p) {
+    typedef typename ElemT<R, CPLX>::type E;
+    __shared__ __align__(16) E As[BK][TM + PAD];
+    __shared__ __align__(16) E Bs[BK][TN + PAD];
+
+    const int tid = threadIdx.x;
+    const uint32_t tilesM = (uint32_t)((p.M + TM - 1) / TM);
+    const uint32_t tilesN = (uint32_t)((p.N + TN - 1) / TN);
+    uint32_t bid = blockIdx.x;
+    const uint32_t bm = bid % tilesM; bid /= tilesM;
+    const uint32_t bn = bid % tilesN; bid /= tilesN;
+    const uint32_t ks = bid % (uint32_t)p.splitk;
+    const uint32_t l = bid / (uint32_t)p.splitk;
+    const uint32_t m0 = bm * TM, n0 = bn * TN;
+    const uint32_t M = (uint32_t)p.M, N = (uint32_t)p.N, K = (uint32_t)p.K;
+    uint32_t k_begin = 0, k_end = K;
+    if (p.splitk > 1) {
+        k_begin = (uint32_t)(ks * p.kchunk);
+        uint64_t ke = (uint64_t)k_begin + (uint64_t)p.kchunk;
+        k_end = ke < K ? (uint32_t)ke : K;
+        if (k_begin > k_end) k_begin = k_end;
+    }
+
+    const E* __restrict__ A = (const E*)p.A + tab(p.al, l);
+    const E* __restrict__ B = (const E*)p.B + tab(p.bl, l);
+
+    // global -> register -> shared load mapping: 2 elements of A and 2 of B per thread and k-tile
+    int a_ml[2], a_kl[2], b_nl[2], b_kl[2];
+    int64_t a_off[2], b_off[2];
+    bool a_ok[2], b_ok[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int e = tid + r * NTHREADS;
+        if (p.a_kfast) { a_kl[r] = e % BK; a_ml[r] = e / BK; } else { a_ml[r] = e % TM; a_kl[r] = e / TM; }
+        if (p.b_kfast) { b_kl[r] = e % BK; b_nl[r] = e / BK; } else { b_nl[r] = e % TN; b_kl[r] = e / TN; }
+        uint32_t m = m0 + a_ml[r], n = n0 + b_nl[r];
+        a_ok[r] = m < M; b_ok[r] = n < N;
+        a_off[r] = a_ok[r] ? tab(p.am, m) : 0;
+        b_off[r] = b_ok[r] ? tab(p.bn, n) : 0;
+    }
+
+    E acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = ezero((E*)0);
+
+    const int tm = tid % 16, tn = tid / 16;
+    E ra[2], rb[2];
+    auto load_tile = [&](uint32_t k0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t ka = k0 + a_kl[r], kb = k0 + b_kl[r];
+            E va = ezero((E*)0), vb = ezero((E*)0);
+            if (a_ok[r] && ka < k_end) va = __ldg(A + a_off[r] + tab(p.ak, ka));
+            if (b_ok[r] && kb < k_end) vb = __ldg(B + b_off[r] + tab(p.bk, kb));
+            ra[r] = p.conjA ? econj(va) : va;
+            rb[r] = p.conjB ? econj(vb) : vb;
+        }
+    };
+
+    if (k_begin < k_end) load_tile(k_begin);
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            As[a_kl[r]][a_ml[r]] = ra[r];
+            Bs[b_kl[r]][b_nl[r]] = rb[r];
+        }
+        __syncthreads();
+        if (k0 + BK < k_end) load_tile(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            E a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[kk][i * 16 + tm];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tn * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) emac(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+
+    if (p.splitk == 1) {
+        E* __restrict__ C = (E*)p.C + tab(p.cl, l);
+        const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
+        int64_t cn_off[4];
+        bool n_ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t n = n0 + tn * 4 + j;
+            n_ok[j] = n < N;
+            cn_off[j] = n_ok[j] ? tab(p.cn, n) : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t m = m0 + i * 16 + tm;
+            if (m >= M) continue;
+            int64_t cm_off = tab(p.cm, m);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (n_ok[j]) store_out(C + cm_off + cn_off[j], acc[i][j], p.alpha, p.beta, has_beta);
+        }
+    } else {
+        E* __restrict__ W = (E*)p.ws;
+        const uint64_t z = (uint64_t)l * (uint64_t)p.splitk + ks;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t m = m0 + i * 16 + tm;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t n = n0 + tn * 4 + j;
+                if (n < N) W[(z * N + n) * M + m] = acc[i][j];
+            }
+        }
+    }
+}
+
+// sums the split-K partials in a fixed order (deterministic) and applies alpha/beta + scatter
+template <typename R, bool CPLX>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const EinsumArgs p) {
+    typedef typename ElemT<R, CPLX>::type E;
+    const uint64_t MN = (uint64_t)p.M * (uint64_t)p.N;
+    const uint64_t total = MN * (uint64_t)p.L;
+    const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t l = (uint32_t)(idx / MN);
+        uint64_t r = idx - (uint64_t)l * MN;
+        uint32_t n = (uint32_t)(r / (uint64_t)p.M);
+        uint32_t m = (uint32_t)(r - (uint64_t)n * (uint64_t)p.M);
+        const E* W = (const E*)p.ws;
+        E s = ezero((E*)0);
+        for (int ks = 0; ks < p.splitk; ks++) s = eadd(s, W[((uint64_t)l * p.splitk + ks) * MN + r]);
+        E* C = (E*)p.C + tab(p.cl, l) + tab(p.cm, m) + tab(p.cn, n);
+        store_out(C, s, p.alpha, p.beta, has_beta);
+    }
+}
+
+}  // namespace
+
+int tnb_choose_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
+                      int64_t* ws_elems) {
+    *kchunk = K;
+    *ws_elems = 0;
+    int64_t tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN) * L;
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    if (tiles >= sms || K < 512) return 1;
+    int64_t want = (2 * sms + tiles - 1) / tiles;          // ~2 CTAs per SM
+    int64_t maxs = K / 128;                                 // at least 128 k per split
+    int64_t s = want < maxs ? want : maxs;
+    const int64_t WS_MAX = (int64_t)1 << 24;                // elements
+    while (s > 1 && s * M * N * L > WS_MAX) s--;
+    if (s <= 1) return 1;
+    int64_t kc = (K + s - 1) / s;
+    kc = (kc + BK - 1) / BK * BK;
+    s = (K + kc - 1) / kc;
+    if (s <= 1) return 1;
+    *kchunk = kc;
+    *ws_elems = s * M * N * L;
+    return (int)s;
+}
+
+template <typename R, bool CPLX>
+static int launch_tile(tnb_ctx* ctx, const EinsumArgs& a) {
+    int64_t tilesM = (a.M + TM - 1) / TM, tilesN = (a.N + TN - 1) / TN;
+    int64_t blocks = tilesM * tilesN * a.L * a.splitk;
+    if (blocks <= 0) return TNB_OK;
+    if (blocks >= ((int64_t)1 << 31)) return tnb_set_error(ctx, TNB_EUNSUPPORTED, "grid too large (%lld tiles)", (long long)blocks);
+    einsum_tile_kernel<R, CPLX><<<(unsigned)blocks, NTHREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+int tnb_launch_einsum_generic(tnb_ctx* ctx, int dtype, const EinsumArgs& args) {
+    switch (dtype) {
+        case TNB_C128: return launch_tile<double, true>(ctx, args);
+        case TNB_C64: return launch_tile<float, true>(ctx, args);
+        case TNB_F64: return launch_tile<double, false>(ctx, args);
+        case TNB_F32: return launch_tile<float, false>(ctx, args);
+    }
+    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "unsupported dtype %d", dtype);
+}
+
+template <typename R, bool CPLX>
+static int launch_reduce(tnb_ctx* ctx, const EinsumArgs& a) {
+    int64_t total = a.M * a.N * a.L;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<R, CPLX><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+int tnb_launch_splitk_reduce(tnb_ctx* ctx, int dtype, const EinsumArgs& args) {
+    switch (dtype) {
+        case TNB_C128: return launch_reduce<double, true>(ctx, args);
+        case TNB_C64: return launch_reduce<float, true>(ctx, args);
+        case TNB_F64: return launch_reduce<double, false>(ctx, args);
+        case TNB_F32: return launch_reduce<float, false>(ctx, args);
+    }
+    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "unsupported dtype %d", dtype);
+}

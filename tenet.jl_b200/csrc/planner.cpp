@@ -1,0 +1,459 @@
+// planner.cpp — host-side planning of pairwise steps and whole contraction paths.
+//
+// What it replaces in the reference: the index bookkeeping Muscle.binary_einsum performs before it
+// calls BLAS (classify inds into free/contracted/batch, permutedims + reshape), and the tree walk of
+// Tangles.contract(tn; path) (call sites: /root/reference/src/Operations/overlap.jl:12,42-47,
+// src/Algorithms/DMRG.jl:10-18).  Instead of materialising permuted operands, the planner emits
+// additive offset tables (tnb_internal.h) and chooses the memory layout of every intermediate so that
+// its single consumer reads it as a dense, M-fastest matrix.
+//
+// Pure host code: no CUDA calls here, so the same code backs the dry-run plans that CPU tests inspect.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include "tnb_internal.h"
+
+namespace {
+
+struct ModeUse {
+    int64_t ext = 1;
+    int64_t sa = 0, sb = 0, sc = 0;
+    bool inA = false, inB = false, inC = false, inSum = false;
+};
+
+std::string fmt_mode(const char* what, int32_t mode) {
+    char buf[128];
+    snprintf(buf, sizeof buf, "%s (mode %d)", what, (int)mode);
+    return buf;
+}
+
+// Build the two-level table of one index group for one tensor.
+// modes are ordered fastest-first; strides[i] is the tensor's stride for modes[i] (0 if absent).
+void build_table(const std::vector<int64_t>& ext, const std::vector<int64_t>& strides, HostTable* t) {
+    const size_t n = ext.size();
+    t->size = 1;
+    for (size_t i = 0; i < n; i++) t->size *= ext[i];
+    // lo prefix
+    size_t npre = 0;
+    int64_t lo = 1;
+    const int64_t LO_MAX = 4096;
+    while (npre < n && (npre == 0 || lo * ext[npre] <= LO_MAX)) {
+        lo *= ext[npre];
+        npre++;
+    }
+    t->lo_size = lo;
+    t->lo.assign((size_t)lo, 0);
+    {
+        std::vector<int64_t> dig(npre, 0);
+        int64_t off = 0;
+        for (int64_t i = 0; i < lo; i++) {
+            t->lo[(size_t)i] = off;
+            // increment mixed-radix counter
+            for (size_t d = 0; d < npre; d++) {
+                dig[d]++;
+                off += strides[d];
+                if (dig[d] < ext[d]) break;
+                off -= strides[d] * ext[d];
+                dig[d] = 0;
+            }
+        }
+    }
+    int64_t hi = t->size / lo;
+    t->hi.assign((size_t)hi, 0);
+    {
+        const size_t nh = n - npre;
+        std::vector<int64_t> dig(nh, 0);
+        int64_t off = 0;
+        for (int64_t i = 0; i < hi; i++) {
+            t->hi[(size_t)i] = off;
+            for (size_t d = 0; d < nh; d++) {
+                dig[d]++;
+                off += strides[npre + d];
+                if (dig[d] < ext[npre + d]) break;
+                off -= strides[npre + d] * ext[npre + d];
+                dig[d] = 0;
+            }
+        }
+    }
+    // affine?
+    t->affine = true;
+    t->stride = 0;
+    if (n > 0) {
+        t->stride = strides[0];
+        int64_t expect = strides[0];
+        for (size_t d = 0; d < n; d++) {
+            if (strides[d] != expect) { t->affine = false; break; }
+            expect *= ext[d];
+        }
+        if (!t->affine) t->stride = 0;
+    }
+}
+
+int64_t min_nonzero_stride(const std::vector<int64_t>& s) {
+    int64_t best = INT64_MAX;
+    for (int64_t v : s) {
+        int64_t a = v < 0 ? -v : v;
+        if (a != 0 && a < best) best = a;
+    }
+    return best;
+}
+
+}  // namespace
+
+int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C,
+                   const std::vector<int32_t>& sum, bool cplx, size_t elem_size, StepSpec* out,
+                   std::string* msg) {
+    std::map<int32_t, ModeUse> use;
+    auto add = [&](const PlanTensor& T, int which) -> int {
+        std::set<int32_t> seen;
+        for (size_t i = 0; i < T.modes.size(); i++) {
+            int32_t m = T.modes[i];
+            if (!seen.insert(m).second) {
+                *msg = fmt_mode("repeated mode inside one tensor", m);
+                return TNB_EINVAL;
+            }
+            if (T.ext[i] < 1) { *msg = fmt_mode("extent < 1", m); return TNB_EINVAL; }
+            auto it = use.find(m);
+            if (it == use.end()) {
+                ModeUse u;
+                u.ext = T.ext[i];
+                it = use.emplace(m, u).first;
+            } else if (it->second.ext != T.ext[i]) {
+                *msg = fmt_mode("extent mismatch", m);
+                return TNB_EINVAL;
+            }
+            ModeUse& u = it->second;
+            if (which == 0) { u.inA = true; u.sa = T.stride[i]; }
+            if (which == 1) { u.inB = true; u.sb = T.stride[i]; }
+            if (which == 2) { u.inC = true; u.sc = T.stride[i]; }
+        }
+        return 0;
+    };
+    int rc;
+    if ((rc = add(A, 0))) return rc;
+    if ((rc = add(B, 1))) return rc;
+    if ((rc = add(C, 2))) return rc;
+    for (int32_t m : sum) {
+        auto it = use.find(m);
+        if (it == use.end()) continue;  // summing a mode nobody carries: no-op
+        it->second.inSum = true;
+    }
+    struct Ent { int32_t mode; int64_t ext, sa, sb, sc; };
+    std::vector<Ent> gm, gn, gk, gl;
+    for (auto& kv : use) {
+        const ModeUse& u = kv.second;
+        Ent e{kv.first, u.ext, u.sa, u.sb, u.sc};
+        if (!u.inA && !u.inB) { *msg = fmt_mode("output mode carried by neither operand", kv.first); return TNB_EINVAL; }
+        if (u.inSum && u.inC) { *msg = fmt_mode("mode is both summed and in the output", kv.first); return TNB_EINVAL; }
+        if (!u.inSum && !u.inC) { *msg = fmt_mode("mode is neither summed nor in the output", kv.first); return TNB_EINVAL; }
+        if (u.ext == 1) continue;  // contributes nothing to addressing
+        if (u.inSum) gk.push_back(e);
+        else if (u.inA && u.inB) gl.push_back(e);
+        else if (u.inA) gm.push_back(e);
+        else gn.push_back(e);
+    }
+    auto by_c = [](const Ent& x, const Ent& y) {
+        if (x.sc != y.sc) return x.sc < y.sc;
+        return x.mode < y.mode;
+    };
+    std::stable_sort(gm.begin(), gm.end(), by_c);
+    std::stable_sort(gn.begin(), gn.end(), by_c);
+    std::stable_sort(gl.begin(), gl.end(), by_c);
+    // K order: by A's stride where A carries the mode, B-only modes afterwards by B's stride.
+    std::stable_sort(gk.begin(), gk.end(), [](const Ent& x, const Ent& y) {
+        bool xa = x.sa != 0, ya = y.sa != 0;
+        if (xa != ya) return xa;
+        if (xa) { if (x.sa != y.sa) return x.sa < y.sa; }
+        else if (x.sb != y.sb) return x.sb < y.sb;
+        return x.mode < y.mode;
+    });
+
+    StepSpec& S = *out;
+    auto mk = [&](const std::vector<Ent>& g, int which, HostTable* t) {
+        std::vector<int64_t> ext, st;
+        for (auto& e : g) {
+            ext.push_back(e.ext);
+            st.push_back(which == 0 ? e.sa : which == 1 ? e.sb : e.sc);
+        }
+        build_table(ext, st, t);
+    };
+    mk(gm, 0, &S.am); mk(gk, 0, &S.ak); mk(gl, 0, &S.al);
+    mk(gn, 1, &S.bn); mk(gk, 1, &S.bk); mk(gl, 1, &S.bl);
+    mk(gm, 2, &S.cm); mk(gn, 2, &S.cn); mk(gl, 2, &S.cl);
+    S.M = S.am.size; S.N = S.bn.size; S.K = S.ak.size; S.L = S.al.size;
+    if (S.M >= (1ll << 31) || S.N >= (1ll << 31) || S.K >= (1ll << 31) || S.L >= 65536) {
+        *msg = "index group too large (M,N,K must be < 2^31, batch < 65536)";
+        return TNB_EUNSUPPORTED;
+    }
+    S.conjA = A.conj; S.conjB = B.conj;
+    {
+        std::vector<int64_t> sm, sk;
+        for (auto& e : gm) sm.push_back(e.sa);
+        for (auto& e : gk) sk.push_back(e.sa);
+        S.a_kfast = min_nonzero_stride(sk) < min_nonzero_stride(sm) ? 1 : 0;
+        sm.clear(); sk.clear();
+        for (auto& e : gn) sm.push_back(e.sb);
+        for (auto& e : gk) sk.push_back(e.sb);
+        S.b_kfast = min_nonzero_stride(sk) < min_nonzero_stride(sm) ? 1 : 0;
+    }
+    S.a_mmajor = S.L == 1 && S.am.affine && (S.M == 1 || S.am.stride == 1) && S.ak.affine &&
+                 (S.K == 1 || S.ak.stride == S.M);
+    S.b_nmajor = S.L == 1 && S.bn.affine && (S.N == 1 || S.bn.stride == 1) && S.bk.affine &&
+                 (S.K == 1 || S.bk.stride == S.N);
+    double macs = (double)S.M * (double)S.N * (double)S.K * (double)S.L;
+    S.flops = (cplx ? 8.0 : 2.0) * macs;
+    auto elems = [](const PlanTensor& T) {
+        int64_t e = 1;
+        for (int64_t x : T.ext) e *= x;
+        return e;
+    };
+    S.a_elems = elems(A); S.b_elems = elems(B); S.c_elems = elems(C);
+    S.bytes = (double)elem_size * ((double)S.a_elems + (double)S.b_elems + (double)S.c_elems);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-path planning
+// ------------------------------------------------------------------------------------------------
+int tnb_plan_build(const tnb_tensor* leaves, int32_t nleaves, const int32_t* steps, int32_t nsteps,
+                   const int32_t* sliced_modes, int32_t nsliced, const tnb_tensor* out, tnb_plan* plan,
+                   std::string* msg) {
+    if (nleaves < 1 || nsteps != nleaves - 1) {
+        *msg = "a path over n leaves needs exactly n-1 pairwise steps (join disconnected parts with outer-product steps)";
+        return TNB_EINVAL;
+    }
+    if (!out) { *msg = "out descriptor is NULL"; return TNB_EINVAL; }
+    const int dtype = out->dtype;
+    const size_t esz = tnb_dtype_size(dtype);
+    if (!esz) { *msg = "unsupported dtype"; return TNB_EUNSUPPORTED; }
+    const bool cplx = tnb_dtype_complex(dtype);
+    plan->dtype = dtype;
+    plan->nleaves = nleaves;
+    plan->nsteps = nsteps;
+    const int nn = nleaves + nsteps;
+    plan->nodes.assign(nn, PlanNode());
+    plan->steps.assign(nsteps, StepSpec());
+
+    std::set<int32_t> sliced(sliced_modes, sliced_modes + nsliced);
+    if ((int)sliced.size() != nsliced) { *msg = "repeated sliced mode"; return TNB_EINVAL; }
+    plan->sliced_modes.assign(sliced_modes, sliced_modes + nsliced);
+    plan->sliced_ext.assign(nsliced, 0);
+
+    std::map<int32_t, int64_t> ext_of;
+    std::map<int32_t, int> total;
+    plan->leaf_buf.resize(nleaves);
+    plan->leaf_off.resize(nleaves);
+    for (int i = 0; i < nleaves; i++) {
+        const tnb_tensor& T = leaves[i];
+        if (T.dtype != dtype) { *msg = "all leaves and the output must share one dtype (promote on the host)"; return TNB_EINVAL; }
+        if (T.rank < 0 || T.rank > TNB_MAX_RANK) { *msg = "leaf rank out of range"; return TNB_EUNSUPPORTED; }
+        PlanNode& nd = plan->nodes[i];
+        nd.leaf = true;
+        nd.t.conj = T.conj;
+        nd.t.offset = T.offset_elems;
+        nd.slice_stride.assign(nsliced, 0);
+        plan->leaf_buf[i] = T.buf;
+        plan->leaf_off[i] = T.offset_elems;
+        std::set<int32_t> seen;
+        for (int r = 0; r < T.rank; r++) {
+            int32_t m = T.mode[r];
+            if (!seen.insert(m).second) { *msg = fmt_mode("repeated mode inside a leaf", m); return TNB_EINVAL; }
+            auto it = ext_of.find(m);
+            if (it == ext_of.end()) ext_of[m] = T.extent[r];
+            else if (it->second != T.extent[r]) { *msg = fmt_mode("extent mismatch between leaves", m); return TNB_EINVAL; }
+            if (T.extent[r] < 1) { *msg = fmt_mode("extent < 1", m); return TNB_EINVAL; }
+            if (sliced.count(m)) {
+                for (int j = 0; j < nsliced; j++)
+                    if (sliced_modes[j] == m) {
+                        nd.slice_stride[j] = T.stride_elems[r];
+                        plan->sliced_ext[j] = T.extent[r];
+                    }
+                nd.dep = true;
+                continue;
+            }
+            nd.t.modes.push_back(m);
+            nd.t.ext.push_back(T.extent[r]);
+            nd.t.stride.push_back(T.stride_elems[r]);
+            nd.elems *= T.extent[r];
+            total[m]++;
+        }
+    }
+    plan->nslices = 1;
+    for (int j = 0; j < nsliced; j++) {
+        if (plan->sliced_ext[j] == 0) { *msg = fmt_mode("sliced mode not carried by any leaf", sliced_modes[j]); return TNB_EINVAL; }
+        plan->nslices *= plan->sliced_ext[j];
+    }
+    // output
+    if (out->rank < 0 || out->rank > TNB_MAX_RANK) { *msg = "output rank out of range"; return TNB_EUNSUPPORTED; }
+    PlanTensor outT;
+    for (int r = 0; r < out->rank; r++) {
+        int32_t m = out->mode[r];
+        if (sliced.count(m)) { *msg = fmt_mode("an output mode cannot be sliced", m); return TNB_EINVAL; }
+        auto it = ext_of.find(m);
+        if (it == ext_of.end()) { *msg = fmt_mode("output mode not carried by any leaf", m); return TNB_EINVAL; }
+        if (it->second != out->extent[r]) { *msg = fmt_mode("output extent mismatch", m); return TNB_EINVAL; }
+        outT.modes.push_back(m);
+        outT.ext.push_back(out->extent[r]);
+        outT.stride.push_back(out->stride_elems[r]);
+        total[m]++;
+    }
+    plan->out_buf = out->buf;
+    plan->out_off = out->offset_elems;
+
+    // bottom-up: mode sets of intermediates
+    std::vector<std::map<int32_t, int>> cnt(nn);
+    for (int i = 0; i < nleaves; i++)
+        for (int32_t m : plan->nodes[i].t.modes) cnt[i][m] = 1;
+    std::vector<std::vector<int32_t>> summed(nsteps);
+    for (int s = 0; s < nsteps; s++) {
+        int a = steps[2 * s], b = steps[2 * s + 1], c = nleaves + s;
+        if (a < 0 || b < 0 || a >= c || b >= c || a == b) { *msg = "step references an id that does not exist yet"; return TNB_EINVAL; }
+        if (plan->nodes[a].consumer >= 0 || plan->nodes[b].consumer >= 0) { *msg = "an id is consumed by two steps"; return TNB_EINVAL; }
+        plan->nodes[a].consumer = c;
+        plan->nodes[b].consumer = c;
+        PlanNode& nd = plan->nodes[c];
+        nd.a = a; nd.b = b;
+        nd.dep = plan->nodes[a].dep || plan->nodes[b].dep;
+        cnt[c] = cnt[a];
+        for (auto& kv : cnt[b]) cnt[c][kv.first] += kv.second;
+        for (auto& kv : cnt[c]) {
+            if (kv.second < total[kv.first]) {
+                nd.t.modes.push_back(kv.first);
+                nd.t.ext.push_back(ext_of[kv.first]);
+                nd.elems *= ext_of[kv.first];
+            } else {
+                summed[s].push_back(kv.first);
+            }
+        }
+        cnt[a].clear();
+        cnt[b].clear();
+        plan->steps[s].a_id = a; plan->steps[s].b_id = b; plan->steps[s].c_id = c;
+        plan->steps[s].hoisted = !nd.dep;
+    }
+    const int root = nn - 1;
+    if (nsteps > 0) {
+        std::set<int32_t> rm(plan->nodes[root].t.modes.begin(), plan->nodes[root].t.modes.end());
+        std::set<int32_t> om(outT.modes.begin(), outT.modes.end());
+        if (rm != om) { *msg = "output modes differ from the open modes of the path result"; return TNB_EINVAL; }
+        plan->nodes[root].t = outT;
+    } else {
+        *msg = "single-leaf network: nothing to contract";
+        return TNB_EINVAL;
+    }
+    if (nsliced > 0 && !plan->nodes[root].dep) { *msg = "sliced modes do not reach the root"; return TNB_EINVAL; }
+
+    // top-down: choose intermediate layouts. For child X of step (A,B)->C:
+    //   X = [ free modes of X in C's order (fastest) | summed modes in the step's K order | batch modes in C's order ]
+    for (int s = nsteps - 1; s >= 0; s--) {
+        const int a = plan->steps[s].a_id, b = plan->steps[s].b_id, c = plan->steps[s].c_id;
+        const PlanTensor& Ct = plan->nodes[c].t;
+        std::vector<size_t> corder(Ct.modes.size());
+        for (size_t i = 0; i < corder.size(); i++) corder[i] = i;
+        std::stable_sort(corder.begin(), corder.end(), [&](size_t x, size_t y) {
+            if (Ct.stride[x] != Ct.stride[y]) return Ct.stride[x] < Ct.stride[y];
+            return Ct.modes[x] < Ct.modes[y];
+        });
+        std::set<int32_t> inA(plan->nodes[a].t.modes.begin(), plan->nodes[a].t.modes.end());
+        std::set<int32_t> inB(plan->nodes[b].t.modes.begin(), plan->nodes[b].t.modes.end());
+        // K order
+        std::vector<int32_t> korder;
+        {
+            const PlanNode* ref = plan->nodes[a].leaf ? &plan->nodes[a] : plan->nodes[b].leaf ? &plan->nodes[b] : nullptr;
+            std::set<int32_t> ks(summed[s].begin(), summed[s].end());
+            if (ref) {
+                std::vector<std::pair<int64_t, int32_t>> v;
+                for (size_t i = 0; i < ref->t.modes.size(); i++)
+                    if (ks.count(ref->t.modes[i])) v.push_back({ref->t.stride[i], ref->t.modes[i]});
+                std::sort(v.begin(), v.end());
+                for (auto& p : v) { korder.push_back(p.second); ks.erase(p.second); }
+            }
+            for (int32_t m : ks) korder.push_back(m);
+        }
+        for (int side = 0; side < 2; side++) {
+            const int x = side == 0 ? a : b;
+            PlanNode& X = plan->nodes[x];
+            if (X.leaf) continue;
+            const std::set<int32_t>& mine = side == 0 ? inA : inB;
+            const std::set<int32_t>& other = side == 0 ? inB : inA;
+            std::vector<int32_t> lay;
+            for (size_t i : corder) {
+                int32_t m = Ct.modes[i];
+                if (mine.count(m) && !other.count(m)) lay.push_back(m);
+            }
+            for (int32_t m : korder) if (mine.count(m)) lay.push_back(m);
+            for (size_t i : corder) {
+                int32_t m = Ct.modes[i];
+                if (mine.count(m) && other.count(m)) lay.push_back(m);
+            }
+            if (lay.size() != X.t.modes.size()) { *msg = "internal: layout size mismatch"; return TNB_EINVAL; }
+            X.t.modes = lay;
+            X.t.ext.clear(); X.t.stride.clear();
+            int64_t st = 1;
+            for (int32_t m : lay) {
+                X.t.ext.push_back(ext_of[m]);
+                X.t.stride.push_back(st);
+                st *= ext_of[m];
+            }
+        }
+    }
+    // per-step GEMM views
+    plan->info = tnb_plan_info{};
+    plan->info.nslices = plan->nslices;
+    for (int s = 0; s < nsteps; s++) {
+        StepSpec& S = plan->steps[s];
+        int rc = tnb_build_step(plan->nodes[S.a_id].t, plan->nodes[S.b_id].t, plan->nodes[S.c_id].t, summed[s],
+                                cplx, esz, &S, msg);
+        if (rc) return rc;
+        if (S.hoisted) {
+            plan->order_hoisted.push_back(s);
+            plan->info.nsteps_hoisted++;
+            plan->info.flops_hoisted += S.flops;
+            plan->info.bytes_hoisted += S.bytes;
+        } else {
+            plan->order_dep.push_back(s);
+            plan->info.nsteps_per_slice++;
+            plan->info.flops_per_slice += S.flops;
+            plan->info.bytes_per_slice += S.bytes;
+        }
+        if (S.c_id != root) plan->info.max_intermediate_elems = std::max(plan->info.max_intermediate_elems, S.c_elems);
+    }
+
+    // arena: first-fit interval allocation over the execution timeline (hoisted steps, then dep steps)
+    {
+        const int64_t align = std::max<int64_t>(1, 1024 / (int64_t)esz);
+        std::vector<int> when(nn, -1);
+        int t = 0;
+        for (int s : plan->order_hoisted) when[nleaves + s] = t++;
+        for (int s : plan->order_dep) when[nleaves + s] = t++;
+        const int T_END = t + 1;
+        struct Live { int64_t off, size; int death; };
+        std::vector<Live> live;
+        std::vector<int> by_birth;
+        for (int s : plan->order_hoisted) by_birth.push_back(nleaves + s);
+        for (int s : plan->order_dep) by_birth.push_back(nleaves + s);
+        int64_t top = 0;
+        for (int id : by_birth) {
+            if (id == root) continue;
+            PlanNode& nd = plan->nodes[id];
+            int birth = when[id];
+            int death = when[nd.consumer];
+            if (!nd.dep && plan->nodes[nd.consumer].dep) death = T_END;  // hoisted value reused by every slice
+            live.erase(std::remove_if(live.begin(), live.end(), [&](const Live& l) { return l.death < birth; }), live.end());
+            std::sort(live.begin(), live.end(), [](const Live& x, const Live& y) { return x.off < y.off; });
+            int64_t size = (nd.elems + align - 1) / align * align;
+            int64_t pos = 0;
+            for (const Live& l : live) {
+                if (pos + size <= l.off) break;
+                pos = std::max(pos, l.off + l.size);
+            }
+            nd.arena_off = pos;
+            live.push_back({pos, size, death});
+            top = std::max(top, pos + size);
+        }
+        plan->arena_elems = top;
+        plan->info.workspace_bytes = top * (int64_t)esz;
+    }
+    return 0;
+}
