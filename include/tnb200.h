@@ -160,6 +160,21 @@ typedef struct tnb_step_info {
 #define TNB_KERNEL_SPLITK    4    /* split-K reduction (M*N tiny, K huge)                    */
 int tnb_plan_get_step(const tnb_plan* plan, int32_t step, tnb_step_info* info);
 
+/* per-step device timing (CUDA events on the context stream; one host sync per slice while enabled) */
+int tnb_plan_profile(tnb_ctx* ctx, tnb_plan* plan, int32_t enable);
+int tnb_plan_get_step_time(const tnb_plan* plan, int32_t step, double* ms_total, int64_t* runs);
+
+/* planning only — no device, no buffers (descriptor buf may be NULL): lets host code and CPU tests inspect the
+ * planner's decisions.  A dry plan cannot be executed.  dump_table: which = 0..8 -> am ak al bn bk bl cm cn cl,
+ * returns the table size and copies min(size, cap) fully expanded offsets.  dump_step: ids[3] = a,b,c node ids,
+ * base[3] = element offset of each operand in its storage, kind[3] = 0 leaf / 1 arena / 2 out,
+ * slice_stride[3][nsliced], conj[2]. */
+int tnb_plan_create_dry(const tnb_tensor* leaves, int32_t nleaves, const int32_t* steps, int32_t nsteps,
+                        const int32_t* sliced_modes, int32_t nsliced, const tnb_tensor* out, tnb_plan** plan);
+int64_t tnb_plan_dump_table(const tnb_plan* plan, int32_t step, int32_t which, int64_t* dst, int64_t cap);
+int tnb_plan_dump_step(const tnb_plan* plan, int32_t step, int32_t* ids, int64_t* base, int32_t* kind,
+                       int64_t* slice_stride, int32_t* conj);
+
 /* one-shot convenience = plan_create + (memset out) + plan_execute + plan_destroy */
 int tnb_contract_path(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nleaves,
                       const int32_t* steps, int32_t nsteps,

@@ -245,12 +245,35 @@ int tnb_plan_create_dry(const tnb_tensor* leaves, int32_t nleaves, const int32_t
 
 int tnb_plan_destroy(tnb_ctx* ctx, tnb_plan* plan) {
     if (!plan) return TNB_OK;
+    for (auto& e : plan->ev) cudaEventDestroy(e);
     if (!plan->dry && ctx) {
         tnb_free(ctx, plan->arena);
         tnb_free(ctx, plan->tables);
         tnb_free(ctx, plan->ws);
     }
     delete plan;
+    return TNB_OK;
+}
+
+// Per-step device timing: when enabled, every step launch is bracketed by CUDA events on the context
+// stream and the host synchronises once per slice to read them (bench.py's roofline numbers).
+int tnb_plan_profile(tnb_ctx* ctx, tnb_plan* plan, int32_t enable) {
+    if (!ctx || !plan || plan->dry) return TNB_EINVAL;
+    cudaSetDevice(ctx->device);
+    if (enable && plan->ev.empty()) {
+        plan->ev.resize(2 * plan->nsteps);
+        for (auto& e : plan->ev) TNB_CUDA_CHECK(ctx, cudaEventCreate(&e));
+    }
+    plan->step_ms.assign(plan->nsteps, 0.0);
+    plan->step_runs.assign(plan->nsteps, 0);
+    plan->profiling = enable != 0;
+    return TNB_OK;
+}
+
+int tnb_plan_get_step_time(const tnb_plan* plan, int32_t step, double* ms_total, int64_t* runs) {
+    if (!plan || step < 0 || step >= plan->nsteps || plan->step_ms.empty()) return TNB_EINVAL;
+    if (ms_total) *ms_total = plan->step_ms[step];
+    if (runs) *runs = plan->step_runs[step];
     return TNB_OK;
 }
 
@@ -330,11 +353,27 @@ int tnb_plan_execute(tnb_ctx* ctx, tnb_plan* P, int64_t slice_begin, int64_t sli
         return (char*)P->arena->ptr + (size_t)nd.arena_off * esz;
     };
     const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+    std::vector<int> timed;   // steps with events in flight
     auto run = [&](int s, bool acc) -> int {
         const StepSpec& S = P->steps[s];
         const double* beta = (S.c_id == root && acc) ? one : zero;
-        return run_step(ctx, dtype, S, dev_blob, operand_ptr(S.a_id), operand_ptr(S.b_id), operand_ptr(S.c_id), one,
-                        beta, P->ws ? P->ws->ptr : nullptr);
+        if (P->profiling) { cudaEventRecord(P->ev[2 * s], ctx->stream); timed.push_back(s); }
+        int r = run_step(ctx, dtype, S, dev_blob, operand_ptr(S.a_id), operand_ptr(S.b_id), operand_ptr(S.c_id), one,
+                         beta, P->ws ? P->ws->ptr : nullptr);
+        if (P->profiling) cudaEventRecord(P->ev[2 * s + 1], ctx->stream);
+        return r;
+    };
+    auto collect = [&]() {
+        if (!P->profiling || timed.empty()) return;
+        cudaStreamSynchronize(ctx->stream);
+        for (int s : timed) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, P->ev[2 * s], P->ev[2 * s + 1]) == cudaSuccess) {
+                P->step_ms[s] += ms;
+                P->step_runs[s]++;
+            }
+        }
+        timed.clear();
     };
     int rc;
     bool acc = accumulate != 0;
@@ -344,16 +383,19 @@ int tnb_plan_execute(tnb_ctx* ctx, tnb_plan* P, int64_t slice_begin, int64_t sli
         if (slice_begin != 0) return TNB_OK;
         for (int s : P->order_hoisted)
             if ((rc = run(s, acc))) return rc;
+        collect();
         return TNB_OK;
     }
     if (slice_begin >= slice_end) return TNB_OK;
     for (int s : P->order_hoisted)
         if ((rc = run(s, false))) return rc;
+    collect();
     for (int64_t sl = slice_begin; sl < slice_end; sl += slice_step) {
         int64_t t = sl;
         for (size_t j = 0; j < ns; j++) { digit[j] = t % P->sliced_ext[j]; t /= P->sliced_ext[j]; }
         for (int s : P->order_dep)
             if ((rc = run(s, acc))) return rc;
+        collect();
         acc = true;
     }
     return TNB_OK;

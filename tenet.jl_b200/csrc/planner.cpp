@@ -254,6 +254,7 @@ int tnb_plan_build(const tnb_tensor* leaves, int32_t nleaves, const int32_t* ste
         nd.t.conj = T.conj;
         nd.t.offset = T.offset_elems;
         nd.slice_stride.assign(nsliced, 0);
+        if (nsliced == 0) nd.dep = true;   // un-sliced network = one slice; nothing is "hoisted"
         plan->leaf_buf[i] = T.buf;
         plan->leaf_off[i] = T.offset_elems;
         std::set<int32_t> seen;

@@ -172,6 +172,11 @@ struct tnb_plan {
     tnb_buf* ws = nullptr;
     int64_t arena_elems = 0, ws_elems = 0;
     std::vector<int64_t> table_blob;      // host copy of all tables
+    // optional per-step device timing (CUDA events on the context stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;          // 2 per step
+    std::vector<double> step_ms;          // accumulated
+    std::vector<int64_t> step_runs;
 };
 
 int tnb_plan_build(const tnb_tensor* leaves, int32_t nleaves, const int32_t* steps, int32_t nsteps,

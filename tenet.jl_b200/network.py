@@ -185,6 +185,19 @@ class ContractionPlan:
         check(self.ctx.handle, self.lib.tnb_plan_execute(self.ctx.handle, self.handle, int(slice_begin),
                                                          int(slice_step), end, 1 if accumulate else 0))
 
+    def profile(self, enable: bool = True):
+        """Bracket every step launch with CUDA events (one host sync per slice while enabled)."""
+        check(self.ctx.handle, self.lib.tnb_plan_profile(self.ctx.handle, self.handle, 1 if enable else 0))
+
+    def step_times(self):
+        """[(ms_total, runs)] per step since profiling was (re-)enabled."""
+        out = []
+        for s in range(self.nsteps):
+            ms, n = C.c_double(), C.c_int64()
+            self.lib.tnb_plan_get_step_time(self.handle, s, C.byref(ms), C.byref(n))
+            out.append((ms.value, n.value))
+        return out
+
     def zero_output(self):
         a = self.out_array
         check(self.ctx.handle, self.lib.tnb_memset_zero(self.ctx.handle, a.buffer.handle, 0, a.size * a.dtype.itemsize))

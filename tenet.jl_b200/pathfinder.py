@@ -341,3 +341,24 @@ def linear_path(n: int) -> List[Tuple[int, int]]:
         steps.append((cur, k))
         cur = n + k - 1
     return steps
+
+
+def search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, target_log2_size: Optional[float] = None,
+           minimize: str = "flops", slice_reopt_trials: int = 0) -> ContractionPath:
+    """Path search + slicing in one call: randomised greedy restarts, then (if the peak intermediate exceeds
+    `target_log2_size`) the greedy slice finder."""
+    p = optimize_path(inputs, sizes, output, ntrials=ntrials, seed=seed, minimize=minimize)
+    if target_log2_size is not None and p.log2_max_size > target_log2_size:
+        p = find_slices(inputs, sizes, output, p, target_log2_size, reoptimize_trials=slice_reopt_trials, seed=seed)
+    return p
+
+
+def load_path(tn_inds_all, filename) -> ContractionPath:
+    """Read a bench_paths/*.json file; `tn_inds_all` = tn.inds("all") maps the stored integer labels back."""
+    import json
+    with open(filename) as f:
+        d = json.load(f)
+    labels = list(tn_inds_all)
+    sliced = tuple(labels[k] for k in d["sliced"])
+    return ContractionPath([tuple(s) for s in d["steps"]], sliced, (), d["log2_macs_per_slice"], d["log2_max_size"],
+                           int(round(2 ** d["nslices_log2"])), d.get("search", {}))
