@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--workload", default="sycamore53_m14")
     ap.add_argument("--slices-per-step", type=int, default=0, help="per GPU; 0 = sized for ~1 s steps")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--c64-mode", default="auto", choices=["auto", "simt", "tf32x3"])
+    ap.add_argument("--c64-mode", default="auto", choices=["auto", "simt", "tf32x3", "tf32x3_fast"])
     ap.add_argument("--dump-steps", default="")
     a = ap.parse_args()
 
@@ -190,7 +190,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = tb.default_context(local_rank)
     if a.c64_mode != "auto":
-        ctx.set_option(tb._lib.TNB_OPT_C64_MODE, {"simt": 0, "tf32x3": 1}[a.c64_mode])
+        ctx.set_option(tb._lib.TNB_OPT_C64_MODE, {"simt": 0, "tf32x3": 1, "tf32x3_fast": 2}[a.c64_mode])
     if world > 1:
         tb.distributed.init_comm(ctx, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)

@@ -44,10 +44,11 @@ extern "C" {
 #define TNB_F32  3
 
 /* precision policy for ComplexF32 / Float32 tensor-core GEMM steps (tnb_ctx_set_option) */
-#define TNB_OPT_C64_MODE     1   /* value: TNB_C64_SIMT | TNB_C64_TF32X3                      */
+#define TNB_OPT_C64_MODE     1   /* value: TNB_C64_SIMT | TNB_C64_TF32X3 | TNB_C64_TF32X3_FAST */
 #define TNB_OPT_FORCE_KERNEL 2   /* value: 0 auto, 1 generic table kernel only (debug/parity) */
 #define TNB_C64_SIMT   0         /* exact FP32 FMA (BLAS-equivalent rounding)                  */
-#define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo operand split, fp32 accumulate  */
+#define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo split; TMEM chunks of 64 k drained into RN fp32 totals (default) */
+#define TNB_C64_TF32X3_FAST 2    /* same, whole K chained in TMEM (RZ accumulate bias ~6e-8 * 0.75 K relative) */
 
 #define TNB_MAX_RANK 64
 
@@ -82,6 +83,8 @@ int tnb_sync(tnb_ctx* ctx);
 void* tnb_ctx_stream(tnb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t tnb_ctx_launch_count(tnb_ctx* ctx);
+/* TNB_KERNEL_* id selected by the most recent tnb_binary_einsum on this context (-1: none yet) */
+int tnb_ctx_last_kernel(tnb_ctx* ctx);
 
 /* ---- device memory: replaces the Array storage behind `parent(tensor)` ---------------------- */
 int tnb_alloc(tnb_ctx* ctx, size_t bytes, tnb_buf** out);   /* stream-ordered caching allocator */

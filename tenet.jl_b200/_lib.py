@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtnb200.so")
 TNB_OK, TNB_EINVAL, TNB_ENOMEM, TNB_ECUDA, TNB_ENCCL, TNB_EUNSUPPORTED = range(6)
 TNB_C128, TNB_C64, TNB_F64, TNB_F32 = range(4)
 TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL = 1, 2
-TNB_C64_SIMT, TNB_C64_TF32X3 = 0, 1
+TNB_C64_SIMT, TNB_C64_TF32X3, TNB_C64_TF32X3_FAST = 0, 1, 2
 KERNEL_NAMES = {0: "generic", 1: "c64_tf32x3", 2: "c128_dmma", 3: "stream", 4: "splitk"}
 
 DTYPE_CODE = {np.dtype(np.complex128): TNB_C128, np.dtype(np.complex64): TNB_C64,
@@ -54,7 +54,7 @@ class tnb_step_info(C.Structure):
 # every symbol include/tnb200.h declares (tests check the library exports each of them)
 ABI_SYMBOLS = [
     "tnb_ctx_create", "tnb_ctx_destroy", "tnb_ctx_set_option", "tnb_last_error", "tnb_sync", "tnb_ctx_stream",
-    "tnb_ctx_launch_count", "tnb_alloc", "tnb_free", "tnb_upload", "tnb_download", "tnb_memset_zero", "tnb_buf_ptr",
+    "tnb_ctx_launch_count", "tnb_ctx_last_kernel", "tnb_alloc", "tnb_free", "tnb_upload", "tnb_download", "tnb_memset_zero", "tnb_buf_ptr",
     "tnb_buf_bytes", "tnb_mem_stats", "tnb_mem_trim", "tnb_binary_einsum", "tnb_binary_einsum_result",
     "tnb_plan_create", "tnb_plan_create_dry", "tnb_plan_execute", "tnb_plan_destroy", "tnb_plan_get_info",
     "tnb_plan_get_step", "tnb_plan_profile", "tnb_plan_get_step_time", "tnb_plan_dump_table", "tnb_plan_dump_step", "tnb_contract_path", "tnb_comm_unique_id",
@@ -86,6 +86,7 @@ def load_library():
             "tnb_sync": (C.c_int, [vp]),
             "tnb_ctx_stream": (vp, [vp]),
             "tnb_ctx_launch_count": (i64, [vp]),
+            "tnb_ctx_last_kernel": (C.c_int, [vp]),
             "tnb_alloc": (C.c_int, [vp, sz, C.POINTER(vp)]),
             "tnb_free": (C.c_int, [vp, vp]),
             "tnb_upload": (C.c_int, [vp, vp, sz, vp, sz]),

@@ -53,6 +53,10 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.tnb_ctx_launch_count(self.handle))
 
+    @property
+    def last_kernel(self) -> str:
+        return _lib.KERNEL_NAMES.get(int(self.lib.tnb_ctx_last_kernel(self.handle)), "none")
+
     def mem_stats(self):
         a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
         check(self.handle, self.lib.tnb_mem_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))

@@ -63,6 +63,40 @@ void read_scalar(int dtype, const void* p, double dflt, double out[2]) {
     }
 }
 
+// Pick the kernel for a planned step (sets kernel/splitk/kchunk/tc fields); returns workspace elements needed.
+int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
+    int64_t kchunk = S.K, ws_elems = 0;
+    S.kernel = TNB_KERNEL_GENERIC;
+    S.splitk = 1;
+    S.kchunk = S.K;
+    S.tc_nt = 0;
+    S.tc_swap = false;
+    const bool force_generic = ctx && ctx->force_generic;
+    if (!force_generic) {
+        int thin = tnb_choose_thin(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
+        if (thin > 0) {
+            S.kernel = TNB_KERNEL_STREAM; S.splitk = thin; S.kchunk = kchunk;
+            return ws_elems;
+        }
+        const bool tc_ok = dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT) &&
+                           (double)S.M * (double)S.N * (double)S.K >= (double)(1ll << 18);
+        if (tc_ok) {
+            int nt = tnb_tc_c64_tile(S.M, S.N, S.K, S.L, S.a_mmajor, S.b_nmajor);
+            int nt_sw = tnb_tc_c64_tile(S.N, S.M, S.K, S.L, S.b_nmajor, S.a_mmajor);
+            if (nt || nt_sw) {
+                S.kernel = TNB_KERNEL_C64_TF32;
+                S.tc_swap = nt_sw > nt;
+                S.tc_nt = S.tc_swap ? nt_sw : nt;
+                return 0;
+            }
+        }
+    }
+    S.splitk = tnb_choose_splitk(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
+    S.kchunk = kchunk;
+    if (S.splitk > 1) S.kernel = TNB_KERNEL_SPLITK;
+    return ws_elems;
+}
+
 // launch one planned step. A/B/C are element pointers already offset to the operand origin.
 int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob, const void* A, const void* B,
              void* C, const double alpha[2], const double beta[2], void* ws) {
@@ -71,7 +105,21 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
     a.A = A; a.B = B; a.C = C;
     a.alpha[0] = alpha[0]; a.alpha[1] = alpha[1];
     a.beta[0] = beta[0]; a.beta[1] = beta[1];
-    if (S.splitk > 1 && ws) {
+    if (S.kernel == TNB_KERNEL_C64_TF32) {
+        int64_t lda = S.K > 1 ? S.ak.stride : S.M, ldb = S.K > 1 ? S.bk.stride : S.N;
+        if (S.tc_swap) {   // C^T = B * A^T : swap operand roles, the offset tables of C swap with them
+            std::swap(a.A, a.B); std::swap(a.M, a.N); std::swap(a.cm, a.cn); std::swap(a.conjA, a.conjB);
+            std::swap(lda, ldb);
+        }
+        return tnb_launch_c64_tc(ctx, a, S.tc_nt, lda, ldb, ctx->c64_mode != TNB_C64_TF32X3_FAST);
+    }
+    if (S.kernel == TNB_KERNEL_STREAM && ws) {
+        a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;
+        int rc = tnb_launch_einsum_thin(ctx, dtype, a);
+        if (rc) return rc;
+        return tnb_launch_splitk_reduce(ctx, dtype, a);
+    }
+    if (S.kernel == TNB_KERNEL_SPLITK && ws) {
         a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;
         int rc = tnb_launch_einsum_generic(ctx, dtype, a);
         if (rc) return rc;
@@ -153,11 +201,10 @@ int tnb_binary_einsum(tnb_ctx* ctx, const tnb_tensor* A, const tnb_tensor* B, co
     if (e != cudaSuccess) { tnb_free(ctx, tb); return tnb_set_error(ctx, TNB_ECUDA, "table upload: %s", cudaGetErrorString(e)); }
     // the blob is pageable host memory: cudaMemcpyAsync has staged it before returning
 
-    int64_t kchunk = S.K, ws_elems = 0;
     tnb_buf* ws = nullptr;
-    S.splitk = tnb_choose_splitk(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
-    S.kchunk = kchunk;
-    if (S.splitk > 1) {
+    int64_t ws_elems = select_kernel(ctx, dtype, S);
+    ctx->last_kernel = S.kernel;
+    if (ws_elems > 0) {
         if ((rc = tnb_alloc(ctx, (size_t)ws_elems * esz, &ws))) { tnb_free(ctx, tb); return rc; }
     }
     double al[2], be[2];
@@ -199,11 +246,7 @@ static int plan_create_impl(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nlea
     const size_t esz = tnb_dtype_size(P->dtype);
     int64_t ws_max = 0;
     for (StepSpec& S : P->steps) {
-        int64_t kchunk = S.K, ws_elems = 0;
-        S.kernel = TNB_KERNEL_GENERIC;
-        S.splitk = tnb_choose_splitk(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
-        S.kchunk = kchunk;
-        if (S.splitk > 1) S.kernel = TNB_KERNEL_SPLITK;
+        int64_t ws_elems = select_kernel(ctx, P->dtype, S);
         ws_max = std::max(ws_max, ws_elems);
         pack_tables(S, P->table_blob);
     }

@@ -72,7 +72,7 @@ int tnb_ctx_set_option(tnb_ctx* ctx, int option, int64_t value) {
     std::lock_guard<std::mutex> g(ctx->mu);
     switch (option) {
         case TNB_OPT_C64_MODE:
-            if (value != TNB_C64_SIMT && value != TNB_C64_TF32X3) return tnb_set_error(ctx, TNB_EINVAL, "bad c64 mode");
+            if (value != TNB_C64_SIMT && value != TNB_C64_TF32X3 && value != TNB_C64_TF32X3_FAST) return tnb_set_error(ctx, TNB_EINVAL, "bad c64 mode");
             ctx->c64_mode = (int)value;
             return TNB_OK;
         case TNB_OPT_FORCE_KERNEL:
@@ -92,6 +92,7 @@ int tnb_sync(tnb_ctx* ctx) {
 
 void* tnb_ctx_stream(tnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t tnb_ctx_launch_count(tnb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int tnb_ctx_last_kernel(tnb_ctx* ctx) { return ctx ? ctx->last_kernel : -1; }
 
 static size_t size_class(size_t bytes) {
     if (bytes < 512) return 512;

@@ -1,0 +1,609 @@
+// kernels_c64_tc.cu — ComplexF32 GEMM-shaped steps on the 5th-gen tensor cores (tcgen05 + TMEM), 3xTF32 split.
+//
+// What it replaces: the BLAS cgemm behind Muscle.binary_einsum for the large steps of a contraction path
+// (/root/reference/src/Operations/overlap.jl:12 -> contract -> binary_einsum).
+//
+//   C[m,n] = sum_k A[m,k] * B[n,k]        A: M-fastest dense [K][M], B: N-fastest dense [K][N]  (planner layouts)
+//
+// Complex product from real sub-GEMMs:  Cre = Are.Bre - Aim.Bim,  Cim = Are.Bim + Aim.Bre.
+// Each real product a*b is evaluated as  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi  with x_hi = tf32(x), x_lo = x - x_hi,
+// i.e. 12 tcgen05.mma.kind::tf32 per 8 complex k per tile, accumulating in fp32 in TMEM.  The relative error of a
+// product is ~2^-21 (the dropped a_lo*b_lo term and the truncation of x_lo to TF32), so results match an FP32
+// cgemm to a few 1e-7 * sqrt(K) — the stated bound for this mode (tests/test_gpu_tc.py).
+//
+// Structure (one CTA per 128 x NT output tile, 288 threads):
+//   warps 0-7  producers: ld.global (coalesced along m/n, 8 B per lane) -> de-interleave re/im, split hi/lo in
+//              registers -> st.shared.v4 into four planes per operand in the UMMA K-major no-swizzle core-matrix
+//              layout -> fence.proxy.async -> mbarrier arrive (full[stage]).  The permuted/split operand is never
+//              written to global memory.
+//   warp 8     one elected thread issues the 12 MMAs per stage (a_negate does the minus sign), tcgen05.commit
+//              frees the stage (empty[stage]) and finally signals the accumulator (acc_full).
+//   warps 0-7  epilogue: tcgen05.ld (32x32b.x16) the two accumulators (Cre: TMEM cols [0,NT), Cim: [NT,2NT)),
+//              alpha/beta, scatter into the consumer's layout through the cm/cn offset tables.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tnb_internal.h"
+
+namespace {
+
+constexpr int TC_BM = 128;          // tile rows (UMMA M, cta_group::1)
+constexpr int TC_BK = 8;            // complex k per stage = UMMA K for tf32
+constexpr int TC_PRODUCERS = 256;   // 8 warps
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B (contiguous 128 B); the two core matrices along K (UMMA K = 8
+// tf32 = 32 B) are LBO apart, consecutive 8-row groups are SBO apart.  Plane layout used here:
+//   byte(row, k) = (row/8)*256 + (k/4)*128 + (row%8)*16 + (k%4)*4      =>  LBO = 128, SBO = 256
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128u >> 4) << 16;   // leading-dimension byte offset (K direction)
+    d |= (uint64_t)(256u >> 4) << 32;   // stride-dimension byte offset (M/N direction)
+    d |= 1ull << 46;                    // descriptor version (Blackwell)
+    return d;                           // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+template <int NT>
+__host__ __device__ constexpr uint32_t make_idesc(bool neg_a) {
+    return (1u << 4)                    // D format F32
+           | (2u << 7) | (2u << 10)     // A, B format TF32
+           | ((neg_a ? 1u : 0u) << 13)  // negate A
+           | (0u << 15) | (0u << 16)    // A, B K-major
+           | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+template <int NT> struct TcSmem {
+    static constexpr int A_PLANE = TC_BM * TC_BK * 4;    // 4 KB
+    static constexpr int B_PLANE = NT * TC_BK * 4;
+    static constexpr int STAGE = 4 * A_PLANE + 4 * B_PLANE;
+    static constexpr int STAGES = (NT == 256) ? 4 : (NT == 128 ? 6 : 8);
+    static constexpr int BAR_OFF = STAGES * STAGE;                 // full[STAGES], empty[STAGES], acc_full
+    static constexpr int TMEM_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
+    static constexpr int CN_OFF = (TMEM_OFF + 4 + 15) / 16 * 16;   // int64 cn offsets [NT]
+    static constexpr int TOTAL = CN_OFF + NT * 8;
+};
+
+struct TcArgs {
+    const float2* A;
+    const float2* B;
+    float2* C;
+    uint32_t M, N, K;
+    int64_t lda, ldb;         // element stride between consecutive k
+    TabRef cm, cn;
+    int32_t conjA, conjB;
+    float alpha[2], beta[2];
+};
+
+__device__ __forceinline__ int64_t tabc(const TabRef& t, uint32_t i) {
+    uint32_t q = i / t.lo_size;
+    uint32_t r = i - q * t.lo_size;
+    return t.hi[q] + t.lo[r];
+}
+
+// one producer work unit: 4 consecutive k of one row -> four planes (re_hi, re_lo, im_hi, im_lo)
+__device__ __forceinline__ void split_store(uint8_t* plane0, int plane_bytes, int row, int kc, const float2 v[4], int conj) {
+    float rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float re = v[i].x, im = conj ? -v[i].y : v[i].y;
+        rh[i] = tf32_hi(re); rl[i] = re - rh[i];
+        ih[i] = tf32_hi(im); il[i] = im - ih[i];
+    }
+    const int off = (row >> 3) * 256 + kc * 128 + (row & 7) * 16;
+    *reinterpret_cast<float4*>(plane0 + off) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+    *reinterpret_cast<float4*>(plane0 + plane_bytes + off) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    *reinterpret_cast<float4*>(plane0 + 2 * plane_bytes + off) = make_float4(ih[0], ih[1], ih[2], ih[3]);
+    *reinterpret_cast<float4*>(plane0 + 3 * plane_bytes + off) = make_float4(il[0], il[1], il[2], il[3]);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TC_THREADS, 1) c64_tf32x3_kernel(const TcArgs p) {
+    using S = TcSmem<NT>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t tilesM = p.M / TC_BM;
+    const uint32_t bm = blockIdx.x % tilesM, bn = blockIdx.x / tilesM;
+    const uint32_t m0 = bm * TC_BM, n0 = bn * NT;
+    const uint32_t nkb = (p.K + TC_BK - 1) / TC_BK;
+
+    const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (S::STAGES + s); };
+    const uint32_t acc_bar = bar0 + 8u * (2 * S::STAGES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
+    int64_t* cn_tab = reinterpret_cast<int64_t*>(smem + S::CN_OFF);
+
+    if (tid == 0) {
+        for (int s = 0; s < S::STAGES; s++) {
+            mbar_init(full_bar(s), TC_PRODUCERS / 32);   // one arrive per producer warp
+            mbar_init(empty_bar(s), 1);                  // tcgen05.commit
+        }
+        mbar_init(acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 2 * NT);
+    for (int i = tid; i < NT; i += TC_THREADS) cn_tab[i] = tabc(p.cn, n0 + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== producers =====================
+        constexpr int A_UNITS = TC_BM * 2 / TC_PRODUCERS;          // 1
+        constexpr int B_UNITS = NT * 2 / TC_PRODUCERS;             // 2 (NT=256), 1 (NT=128)
+        static_assert(A_UNITS >= 1 && B_UNITS >= 1, "tile too small for the producer mapping");
+        float2 va[A_UNITS][4], vb[B_UNITS][4];
+        auto load = [&](uint32_t kb) {
+            const uint32_t k0 = kb * TC_BK;
+#pragma unroll
+            for (int u = 0; u < A_UNITS; u++) {
+                int unit = tid + u * TC_PRODUCERS;
+                int row = unit % TC_BM, kc = unit / TC_BM;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t k = k0 + kc * 4 + i;
+                    va[u][i] = k < p.K ? __ldg(p.A + (int64_t)k * p.lda + (m0 + row)) : make_float2(0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < B_UNITS; u++) {
+                int unit = tid + u * TC_PRODUCERS;
+                int row = unit % NT, kc = unit / NT;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint32_t k = k0 + kc * 4 + i;
+                    vb[u][i] = k < p.K ? __ldg(p.B + (int64_t)k * p.ldb + (n0 + row)) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        if (nkb > 0) load(0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (uint32_t kb = 0; kb < nkb; kb++) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            uint8_t* sa = smem + stage * S::STAGE;
+            uint8_t* sb = sa + 4 * S::A_PLANE;
+#pragma unroll
+            for (int u = 0; u < A_UNITS; u++) {
+                int unit = tid + u * TC_PRODUCERS;
+                split_store(sa, S::A_PLANE, unit % TC_BM, unit / TC_BM, va[u], p.conjA);
+            }
+#pragma unroll
+            for (int u = 0; u < B_UNITS; u++) {
+                int unit = tid + u * TC_PRODUCERS;
+                split_store(sb, S::B_PLANE, unit % NT, unit / NT, vb[u], p.conjB);
+            }
+            if (kb + 1 < nkb) load(kb + 1);        // next stage's global loads fly while the MMAs run
+            fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor-core proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ===================== epilogue =====================
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t row = q * 32 + lane;
+        const int64_t cm_off = tabc(p.cm, m0 + row);
+        float2* __restrict__ Crow = p.C + cm_off;
+        const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
+        const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+        constexpr int COLS = NT / 2;
+        for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 16) {
+            uint32_t re[16], im[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld16(taddr, re);
+            tmem_ld16(taddr + NT, im);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                float2 v = make_float2(ar * xr - ai * xi, ar * xi + ai * xr);
+                float2* dst = Crow + cn_tab[c0 + j];
+                if (has_beta) {
+                    float2 o = *dst;
+                    v.x += br * o.x - bi * o.y;
+                    v.y += br * o.y + bi * o.x;
+                }
+                *dst = v;
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ===================== MMA issuer (warp 8) =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
+            const uint32_t d_re = tmem_base, d_im = tmem_base + NT;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (uint32_t kb = 0; kb < nkb; kb++) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * S::STAGE);
+                const uint32_t sb = sa + 4 * S::A_PLANE;
+                const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + S::A_PLANE),
+                               a_ih = make_smem_desc(sa + 2 * S::A_PLANE), a_il = make_smem_desc(sa + 3 * S::A_PLANE);
+                const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + S::B_PLANE),
+                               b_ih = make_smem_desc(sb + 2 * S::B_PLANE), b_il = make_smem_desc(sb + 3 * S::B_PLANE);
+                const uint32_t acc = kb > 0 ? 1u : 0u;
+                // Cre = Are.Bre - Aim.Bim     (small cross terms first, hi*hi last)
+                umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
+                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
+                umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                // Cim = Are.Bim + Aim.Bre
+                umma_tf32(d_im, a_rh, b_il, IDESC, acc);
+                umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
+                umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                umma_commit(empty_bar(stage));     // implies tcgen05.fence::before_thread_sync
+                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * NT);
+    }
+}
+
+template <int NT>
+int launch_tc(tnb_ctx* ctx, const TcArgs& a) {
+    using S = TcSmem<NT>;
+    static bool configured[16] = {false};
+    if (!configured[ctx->device & 15]) {
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured[ctx->device & 15] = true;
+    }
+    const unsigned grid = (a.M / TC_BM) * (a.N / NT);
+    c64_tf32x3_kernel<NT><<<grid, TC_THREADS, S::TOTAL, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Chunked-accumulation variant (the default): same data path, 128 x 128 tile, but the TMEM accumulators only
+// ever hold a CHUNK of KCB k-blocks.  The tensor core adds into its FP32 accumulator with round-toward-zero, a
+// bias that grows linearly with the number of chained MMAs (measured: ~6e-8 * #MMAs relative, i.e. 1.5e-5 at
+// K = 1024 when the whole K is chained — see profiles/r1_tc_accuracy.md).  Here two TMEM accumulator sets
+// ping-pong: while the MMA warp fills one with chunk c+1, the 16 worker warps drain chunk c with tcgen05.ld and
+// add it into per-thread FP32 totals with round-to-nearest.  Chain length = 6*KCB MMAs => ~3e-6 relative.
+//
+//   warps 0-15 workers: (a) producers, one (row, 4k) unit per thread and k-block (warps 0-7 feed A, 8-15 feed B),
+//                       (b) every KCB k-blocks drain the finished chunk into 64 total registers
+//                           (thread = row, 32 complex columns), (c) epilogue scatter of the totals.
+//   warp 16    MMA issuer.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ACC_NT = 128;
+constexpr int ACC_WORKERS = 512;              // warps 0-15
+constexpr int ACC_THREADS = ACC_WORKERS + 64; // + warp 16 (MMA issuer) + warp 17 (bulk-copy issuer)
+constexpr int ACC_KCB = 8;                    // k-blocks (of 8 complex k) per TMEM chunk
+constexpr int ACC_RAW_STAGES = 6;             // raw (interleaved complex) operand tiles landed by cp.async.bulk
+constexpr int ACC_PL_STAGES = 3;              // split planes consumed by tcgen05.mma
+
+struct AccSmem {
+    static constexpr int A_PLANE = TC_BM * TC_BK * 4;                  // 4 KB
+    static constexpr int B_PLANE = ACC_NT * TC_BK * 4;
+    static constexpr int PL_STAGE = 4 * A_PLANE + 4 * B_PLANE;         // 32 KB
+    static constexpr int RAW_HALF = TC_BK * TC_BM * 8;                 // 8 KB: [8 k][128 rows] float2
+    static constexpr int RAW_STAGE = 2 * RAW_HALF;                     // A then B
+    static constexpr int RAW_OFF = ACC_PL_STAGES * PL_STAGE;
+    static constexpr int BAR_OFF = RAW_OFF + ACC_RAW_STAGES * RAW_STAGE;
+    // raw_full[R], raw_empty[R], pl_full[P], pl_empty[P], accfull[2], accempty[2]
+    static constexpr int NBARS = 2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 4;
+    static constexpr int TMEM_OFF = BAR_OFF + NBARS * 8;
+    static constexpr int CN_OFF = (TMEM_OFF + 4 + 15) / 16 * 16;
+    static constexpr int TOTAL = CN_OFF + ACC_NT * 8;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier; no tensor map needed
+// because a tile row (128 consecutive m or n at fixed k) is contiguous in the planner's layouts.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const TcArgs p) {
+    using S = AccSmem;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t tilesM = p.M / TC_BM;
+    const uint32_t bm = blockIdx.x % tilesM, bn = blockIdx.x / tilesM;
+    const uint32_t m0 = bm * TC_BM, n0 = bn * ACC_NT;
+    const uint32_t nkb = p.K / TC_BK;                 // K % 8 == 0 (eligibility)
+    const uint32_t nchunks = (nkb + ACC_KCB - 1) / ACC_KCB;
+
+    const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
+    auto raw_full = [&](int s) { return bar0 + 8u * s; };
+    auto raw_empty = [&](int s) { return bar0 + 8u * (ACC_RAW_STAGES + s); };
+    auto pl_full = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + s); };
+    auto pl_empty = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + ACC_PL_STAGES + s); };
+    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + s); };
+    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
+    int64_t* cn_tab = reinterpret_cast<int64_t*>(smem + S::CN_OFF);
+
+    if (tid == 0) {
+        for (int s = 0; s < ACC_RAW_STAGES; s++) {
+            mbar_init(raw_full(s), 1);                    // expect_tx arrive of the copy issuer
+            mbar_init(raw_empty(s), ACC_WORKERS / 32);
+        }
+        for (int s = 0; s < ACC_PL_STAGES; s++) {
+            mbar_init(pl_full(s), ACC_WORKERS / 32);
+            mbar_init(pl_empty(s), 1);                    // tcgen05.commit
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(accfull_bar(s), 1);
+            mbar_init(accempty_bar(s), ACC_WORKERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+    for (int i = tid; i < ACC_NT; i += ACC_THREADS) cn_tab[i] = tabc(p.cn, n0 + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 16) {
+        // ---- worker: raw tile -> split planes, chunk drain, epilogue ----
+        const bool feeds_a = tid < 256;
+        const int u = feeds_a ? tid : tid - 256;
+        const int prow = u & 127, pkc = u >> 7;
+        const int pconj = feeds_a ? p.conjA : p.conjB;
+        const int plane_bytes = feeds_a ? S::A_PLANE : S::B_PLANE;
+        const int plane_base = feeds_a ? 0 : 4 * S::A_PLANE;
+        const int raw_base = S::RAW_OFF + (feeds_a ? 0 : S::RAW_HALF) + (pkc * 4 * TC_BM + prow) * 8;
+        const int q = warp & 3, g = warp >> 2;        // TMEM lane quarter, 32-column group
+        float tr[32], ti[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) { tr[j] = 0.f; ti[j] = 0.f; }
+        auto drain = [&](uint32_t c) {
+            const uint32_t set = c & 1;
+            mbar_wait(accfull_bar(set), (c >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(g * 32);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t r[16], im[16];
+                tmem_ld16(taddr + h * 16, r);
+                tmem_ld16(taddr + 128 + h * 16, im);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    tr[h * 16 + j] += __uint_as_float(r[j]);
+                    ti[h * 16 + j] += __uint_as_float(im[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accempty_bar(set));
+        };
+
+        int rs = 0, ps = 0;
+        uint32_t rphase = 0, pphase = 0, drained = 0;
+        for (uint32_t kb = 0; kb < nkb; kb++) {
+            if (kb % ACC_KCB == 0) {
+                const uint32_t c = kb / ACC_KCB;
+                while (drained + 2 <= c) { drain(drained); drained++; }
+            }
+            mbar_wait(raw_full(rs), rphase);
+            float2 v[4];
+            const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+            mbar_wait(pl_empty(ps), pphase ^ 1);
+            split_store(smem + ps * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v, pconj);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(pl_full(ps));
+                mbar_arrive(raw_empty(rs));
+            }
+            if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
+            if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
+        }
+        while (drained < nchunks) { drain(drained); drained++; }
+
+        // ---- epilogue: totals -> alpha/beta -> scatter ----
+        const uint32_t row = q * 32 + lane;
+        float2* __restrict__ Crow = p.C + tabc(p.cm, m0 + row);
+        const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
+        const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
+            float2* dst = Crow + cn_tab[g * 32 + j];
+            if (has_beta) {
+                float2 old = *dst;
+                o.x += br * old.x - bi * old.y;
+                o.y += br * old.y + bi * old.x;
+            }
+            *dst = o;
+        }
+    } else if (warp == 16) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
+            int ps = 0;
+            uint32_t pphase = 0;
+            for (uint32_t kb = 0; kb < nkb; kb++) {
+                const uint32_t c = kb / ACC_KCB, set = c & 1;
+                const bool first = (kb % ACC_KCB) == 0;
+                if (first && c >= 2) {
+                    mbar_wait(accempty_bar(set), ((c >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
+                mbar_wait(pl_full(ps), pphase);
+                tc_fence_after();
+                const uint32_t d_re = tmem_base + set * 256u, d_im = d_re + 128u;
+                const uint32_t sa = smem_u32(smem + ps * S::PL_STAGE);
+                const uint32_t sb = sa + 4 * S::A_PLANE;
+                const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + S::A_PLANE),
+                               a_ih = make_smem_desc(sa + 2 * S::A_PLANE), a_il = make_smem_desc(sa + 3 * S::A_PLANE);
+                const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + S::B_PLANE),
+                               b_ih = make_smem_desc(sb + 2 * S::B_PLANE), b_il = make_smem_desc(sb + 3 * S::B_PLANE);
+                const uint32_t acc = first ? 0u : 1u;
+                umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
+                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
+                umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                umma_tf32(d_im, a_rh, b_il, IDESC, acc);
+                umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
+                umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                umma_commit(pl_empty(ps));
+                if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(set));
+                if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B ----
+        int rs = 0;
+        uint32_t rphase = 0;
+        const bool is_a = lane < 8;
+        const int krow = lane & 7;
+        const float2* src = is_a ? p.A + m0 : p.B + n0;
+        const int64_t ld = is_a ? p.lda : p.ldb;
+        for (uint32_t kb = 0; kb < nkb; kb++) {
+            mbar_wait(raw_empty(rs), rphase ^ 1);
+            if (lane == 0) mbar_expect_tx(raw_full(rs), S::RAW_STAGE);
+            __syncwarp();
+            if (lane < 16) {
+                const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (is_a ? 0 : S::RAW_HALF) + krow * TC_BM * 8);
+                bulk_g2s(dst, src + (int64_t)(kb * TC_BK + krow) * ld, TC_BM * 8, raw_full(rs));
+            }
+            if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
+    static bool configured[16] = {false};
+    if (!configured[ctx->device & 15]) {
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AccSmem::TOTAL));
+        configured[ctx->device & 15] = true;
+    }
+    const unsigned grid = (a.M / TC_BM) * (a.N / ACC_NT);
+    c64_tf32x3_acc_kernel<<<grid, ACC_THREADS, AccSmem::TOTAL, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+// cp.async.bulk needs 16-byte aligned rows: even leading dimensions, 16-byte aligned bases, K a multiple of 8
+bool tc_acc_ok(const TcArgs& a) {
+    return a.N % ACC_NT == 0 && a.K % TC_BK == 0 && (a.lda % 2) == 0 && (a.ldb % 2) == 0 &&
+           ((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.B % 16) == 0;
+}
+
+
+}  // namespace
+
+// Eligibility: complex64, no batch, both operands dense with the free index fastest, tile-aligned sizes.
+// Returns the N tile (256/128/64) or 0.
+int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor) {
+    if (L != 1 || !a_mmajor || !b_nmajor) return 0;
+    if (M % TC_BM != 0 || K < 16) return 0;
+    if (M / TC_BM >= (1 << 20)) return 0;
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    return 0;
+}
+
+int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked) {
+    TcArgs a;
+    a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
+    a.M = (uint32_t)e.M; a.N = (uint32_t)e.N; a.K = (uint32_t)e.K;
+    a.lda = lda; a.ldb = ldb;
+    a.cm = e.cm; a.cn = e.cn;
+    a.conjA = e.conjA; a.conjB = e.conjB;
+    a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
+    a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
+    if (chunked && tc_acc_ok(a)) return launch_tc_acc(ctx, a);
+    if (nt == 256) return launch_tc<256>(ctx, a);
+    if (nt == 128) return launch_tc<128>(ctx, a);
+    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "no tcgen05 tile for N tile %d", nt);
+}

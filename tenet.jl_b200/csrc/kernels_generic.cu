@@ -215,7 +215,136 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const EinsumArgs p) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// "thin" reduction kernel: M*N <= 16 (amplitude-closing dot products, tiny environments), K huge, L == 1.
+// HBM-bound: every CTA streams a contiguous chunk of K with all threads along k (coalesced when the operand
+// is k-fastest, which the planner's [free | contracted] layout guarantees when there are no free modes),
+// keeps the MxN partial sums in registers, block-reduces them and writes one partial per CTA; the
+// split-K reducer above then sums the partials in a fixed order (deterministic).
+// Algorithmic bytes per launch: sizeof(T) * (M + N) * K.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int THIN_MAX = 4;       // M, N <= 4
+constexpr int THIN_THREADS = 256;
+constexpr int THIN_UNROLL = 4;
+
+template <typename R, bool CPLX>
+__global__ void __launch_bounds__(THIN_THREADS) einsum_thin_kernel(const EinsumArgs p) {
+    typedef typename ElemT<R, CPLX>::type E;
+    const uint32_t M = (uint32_t)p.M, N = (uint32_t)p.N, K = (uint32_t)p.K;
+    const E* __restrict__ A = (const E*)p.A;
+    const E* __restrict__ B = (const E*)p.B;
+    int64_t am[THIN_MAX], bn[THIN_MAX];
+#pragma unroll
+    for (int i = 0; i < THIN_MAX; i++) {
+        am[i] = i < (int)M ? tab(p.am, i) : 0;
+        bn[i] = i < (int)N ? tab(p.bn, i) : 0;
+    }
+    E acc[THIN_MAX][THIN_MAX];
+#pragma unroll
+    for (int i = 0; i < THIN_MAX; i++)
+#pragma unroll
+        for (int j = 0; j < THIN_MAX; j++) acc[i][j] = ezero((E*)0);
+
+    const uint64_t kb = (uint64_t)blockIdx.x * (uint64_t)p.kchunk;
+    uint64_t ke64 = kb + (uint64_t)p.kchunk;
+    const uint32_t k_begin = kb < K ? (uint32_t)kb : K;
+    const uint32_t k_end = ke64 < K ? (uint32_t)ke64 : K;
+    const bool aff = p.ak.affine && p.bk.affine;
+    for (uint32_t k0 = k_begin + threadIdx.x; k0 < k_end; k0 += THIN_THREADS * THIN_UNROLL) {
+        E a[THIN_UNROLL][THIN_MAX], b[THIN_UNROLL][THIN_MAX];
+#pragma unroll
+        for (int u = 0; u < THIN_UNROLL; u++) {
+            uint32_t k = k0 + u * THIN_THREADS;
+            bool ok = k < k_end;
+            int64_t oa = 0, ob = 0;
+            if (ok) {
+                if (aff) { oa = (int64_t)k * p.ak.stride; ob = (int64_t)k * p.bk.stride; }
+                else { oa = tab(p.ak, k); ob = tab(p.bk, k); }
+            }
+#pragma unroll
+            for (int i = 0; i < THIN_MAX; i++) {
+                a[u][i] = (ok && i < (int)M) ? __ldg(A + am[i] + oa) : ezero((E*)0);
+                b[u][i] = (ok && i < (int)N) ? __ldg(B + bn[i] + ob) : ezero((E*)0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < THIN_UNROLL; u++)
+#pragma unroll
+            for (int i = 0; i < THIN_MAX; i++) {
+                E av = p.conjA ? econj(a[u][i]) : a[u][i];
+#pragma unroll
+                for (int j = 0; j < THIN_MAX; j++) {
+                    E bv = p.conjB ? econj(b[u][j]) : b[u][j];
+                    emac(acc[i][j], av, bv);
+                }
+            }
+    }
+    // block reduction through shared memory, fixed order
+    __shared__ E red[THIN_THREADS / 32][THIN_MAX * THIN_MAX];
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+#pragma unroll
+    for (int i = 0; i < THIN_MAX; i++)
+#pragma unroll
+        for (int j = 0; j < THIN_MAX; j++) {
+            E v = acc[i][j];
+            if (i < (int)M && j < (int)N) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    if constexpr (CPLX) {
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+                        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+                    } else {
+                        v += __shfl_xor_sync(0xffffffffu, v, o);
+                    }
+                }
+                if (lane == 0) red[warp][i * THIN_MAX + j] = v;
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x < THIN_MAX * THIN_MAX) {
+        int i = threadIdx.x / THIN_MAX, j = threadIdx.x % THIN_MAX;
+        if (i < (int)M && j < (int)N) {
+            E s = ezero((E*)0);
+            for (int w = 0; w < THIN_THREADS / 32; w++) s = eadd(s, red[w][threadIdx.x]);
+            // partial layout expected by splitk_reduce_kernel: ws[(ks*N + n)*M + m]
+            ((E*)p.ws)[((uint64_t)blockIdx.x * N + j) * M + i] = s;
+        }
+    }
+}
+
 }  // namespace
+
+// thin path: returns number of CTAs (= splitk) or 0 if not applicable
+int tnb_choose_thin(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems) {
+    if (L != 1 || M > THIN_MAX || N > THIN_MAX || K < 4096) return 0;
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    int64_t ctas = sms * 8;
+    int64_t per = THIN_THREADS * THIN_UNROLL;
+    int64_t kc = (K + ctas - 1) / ctas;
+    kc = (kc + per - 1) / per * per;
+    ctas = (K + kc - 1) / kc;
+    *kchunk = kc;
+    *ws_elems = ctas * M * N;
+    return (int)ctas;
+}
+
+template <typename R, bool CPLX>
+static int launch_thin(tnb_ctx* ctx, const EinsumArgs& a) {
+    einsum_thin_kernel<R, CPLX><<<(unsigned)a.splitk, THIN_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args) {
+    switch (dtype) {
+        case TNB_C128: return launch_thin<double, true>(ctx, args);
+        case TNB_C64: return launch_thin<float, true>(ctx, args);
+        case TNB_F64: return launch_thin<double, false>(ctx, args);
+        case TNB_F32: return launch_thin<float, false>(ctx, args);
+    }
+    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "unsupported dtype %d", dtype);
+}
 
 int tnb_choose_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
                       int64_t* ws_elems) {

@@ -158,8 +158,17 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         if (x.sc != y.sc) return x.sc < y.sc;
         return x.mode < y.mode;
     };
-    std::stable_sort(gm.begin(), gm.end(), by_c);
-    std::stable_sort(gn.begin(), gn.end(), by_c);
+    // Free modes are enumerated in the order the OPERAND stores them (so that a dense operand reads as an
+    // M-/N-fastest matrix and qualifies for the tensor-core kernels); the output is scattered through cm/cn.
+    // For intermediates the planner lays the operand out in the output's order, so both orders coincide.
+    std::stable_sort(gm.begin(), gm.end(), [](const Ent& x, const Ent& y) {
+        if (x.sa != y.sa) return x.sa < y.sa;
+        return x.mode < y.mode;
+    });
+    std::stable_sort(gn.begin(), gn.end(), [](const Ent& x, const Ent& y) {
+        if (x.sb != y.sb) return x.sb < y.sb;
+        return x.mode < y.mode;
+    });
     std::stable_sort(gl.begin(), gl.end(), by_c);
     // K order: by A's stride where A carries the mode, B-only modes afterwards by B's stride.
     std::stable_sort(gk.begin(), gk.end(), [](const Ent& x, const Ent& y) {

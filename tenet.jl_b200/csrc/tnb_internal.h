@@ -71,6 +71,8 @@ struct StepSpec {
     // fast-kernel eligibility facts (filled by the planner)
     bool a_mmajor = false;   // A[m + M*k] exactly (dense, M fastest), no conj needed handled separately
     bool b_nmajor = false;
+    int32_t tc_nt = 0;       // tcgen05 kernel: N tile (256/128), 0 = not used
+    bool tc_swap = false;    // tcgen05 kernel: operands swapped (C^T = B A^T)
 };
 
 struct tnb_buf {
@@ -91,8 +93,9 @@ struct tnb_ctx {
     size_t in_use = 0, cached = 0, peak = 0;
     int64_t launches = 0;
     int sm_count = 148;
-    int c64_mode = TNB_C64_SIMT;
+    int c64_mode = TNB_C64_TF32X3;
     int force_generic = 0;
+    int last_kernel = -1;    // kernel id chosen by the most recent tnb_binary_einsum (introspection)
     // comm
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
@@ -126,6 +129,12 @@ int tnb_launch_splitk_reduce(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
 // decide split-K factor for the generic kernel; returns splitk (>=1) and sets kchunk, ws elems needed
 int tnb_choose_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
                       int64_t* ws_elems);
+
+int tnb_choose_thin(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);
+int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
+// kernels_c64_tc.cu
+int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
+int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);
 
 // planner.cpp  (pure host code; also used by the dry-run plan that CPU tests inspect)
 struct PlanTensor {

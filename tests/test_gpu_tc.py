@@ -1,0 +1,86 @@
+"""GPU parity of the specialised kernels against the oracle AND against the generic table kernel:
+  * c64_tf32x3 (tcgen05 + TMEM, 3xTF32 split): stated bound — max-abs error relative to the largest |C| entry
+    below 2e-5 for K <= 8192 with O(1) Gaussian entries, and within 20x of the exact-FP32 SIMT kernel's own error.
+  * thin reduction kernel (M,N <= 4, huge K) and split-K path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def crand(rng, shape, dt=np.complex64):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dt)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 40), (128, 128, 16), (384, 512, 200), (512, 512, 1024),
+                                   (256, 1024, 8192)])
+def test_tc_matches_oracle(ctx, M, N, K):
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(M + N + K)
+    a, b = crand(rng, (M, K)), crand(rng, (N, K))
+    c = tb.binary_einsum(tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("n", "k")))
+    assert ctx.last_kernel == "c64_tf32x3"
+    ref = a.astype(np.complex128) @ b.astype(np.complex128).T
+    got = c.parent
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-5, f"rel err {err:.2e}"
+    # same step on the exact-FP32 generic kernel: both must sit within FP32 noise of the c128 truth
+    ctx.set_option(tb._lib.TNB_OPT_FORCE_KERNEL, 1)
+    try:
+        c2 = tb.binary_einsum(tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("n", "k")))
+        assert ctx.last_kernel in ("generic", "splitk")
+    finally:
+        ctx.set_option(tb._lib.TNB_OPT_FORCE_KERNEL, 0)
+    err2 = np.abs(c2.parent - ref).max() / np.abs(ref).max()
+    assert err2 < 2e-5
+    assert err < 20 * max(err2, 1e-7), f"3xTF32 error {err:.2e} vs FP32-SIMT error {err2:.2e}"
+
+
+def test_tc_conj_swap_and_scatter(ctx):
+    """conj flags, operand swap (M not a multiple of 128 but N is), multi-mode free/contracted groups, custom
+    output order (scattered epilogue)."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(1)
+    a = crand(rng, (4, 8, 4, 16, 8))          # m1 m2 m3 | k1 k2   -> M = 128, K = 128
+    b = crand(rng, (16, 4, 4, 16, 8))         # n1 n2 n3 | k1 k2   -> N = 256
+    ta = tb.Tensor(a, ("m1", "m2", "m3", "k1", "k2"))
+    tb_ = tb.Tensor(b, ("n1", "n2", "n3", "k1", "k2")).conj()
+    ref = np.einsum("abcxy,defxy->abcdef", a.astype(np.complex128), np.conj(b).astype(np.complex128))
+    for out in [None, ("n2", "m1", "n1", "m3", "m2", "n3")]:
+        c = tb.binary_einsum(ta, tb_, out=out)
+        assert ctx.last_kernel == "c64_tf32x3"
+        r = ref if out is None else np.einsum("abcdef->eadcbf", ref)
+        assert np.abs(c.parent - r).max() / np.abs(r).max() < 2e-5
+    a2, b2 = crand(rng, (64, 32)), crand(rng, (256, 32))     # M = 64 -> swapped roles
+    c = tb.binary_einsum(tb.Tensor(a2, ("m", "k")).conj(), tb.Tensor(b2, ("n", "k")))
+    ref = np.conj(a2).astype(np.complex128) @ b2.astype(np.complex128).T
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 2e-5
+
+
+def test_simt_mode_option(ctx):
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(2)
+    a, b = crand(rng, (128, 64)), crand(rng, (256, 64))
+    ctx.set_option(tb._lib.TNB_OPT_C64_MODE, tb._lib.TNB_C64_SIMT)
+    try:
+        tb.binary_einsum(tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("n", "k")))
+        assert ctx.last_kernel == "generic"
+    finally:
+        ctx.set_option(tb._lib.TNB_OPT_C64_MODE, tb._lib.TNB_C64_TF32X3)
+
+
+@pytest.mark.parametrize("dt,tol", [(np.complex64, 1e-5), (np.complex128, 1e-13), (np.float64, 1e-13)])
+@pytest.mark.parametrize("M,N", [(1, 1), (2, 3), (4, 4), (1, 4)])
+def test_thin_reduction(ctx, dt, tol, M, N):
+    """amplitude-closing dot products: M*N <= 16, K = 2^20 (+ a ragged K)."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(3)
+    for K in (1 << 20, 777777):
+        if np.dtype(dt).kind == "c":
+            a, b = crand(rng, (K, M), dt), crand(rng, (K, N), dt)
+        else:
+            a, b = rng.standard_normal((K, M)).astype(dt), rng.standard_normal((K, N)).astype(dt)
+        c = tb.binary_einsum(tb.Tensor(a, ("k", "m")), tb.Tensor(b, ("k", "n")))
+        assert ctx.last_kernel == "stream"
+        ref = a.astype(np.complex128).T @ b.astype(np.complex128)
+        assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
