@@ -103,10 +103,20 @@ __host__ __device__ constexpr uint32_t make_idesc(bool neg_a) {
            | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// x_hi = x with the low 13 mantissa bits cleared (what the tensor core would read anyway), x_lo = x - x_hi exactly.
+// One LOP3 instead of the multi-instruction emulation of cvt.rna.tf32 on sm_100a; the split stays error-free and
+// x_lo (<= 2^-10 |x|) is truncated to TF32 by the MMA, leaving a representation error <= 2^-21 |x|.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// L2-friendly tile order: groups of RASTER_GM m-tiles sweep all n-tiles, so the CTAs of one wave share A and B tiles.
+constexpr uint32_t RASTER_GM = 8;
+__device__ __forceinline__ void raster(uint32_t pid, uint32_t tilesM, uint32_t tilesN, uint32_t& bm, uint32_t& bn) {
+    const uint32_t per_group = RASTER_GM * tilesN;
+    const uint32_t group = pid / per_group, first_m = group * RASTER_GM;
+    const uint32_t gsize = (tilesM - first_m) < RASTER_GM ? (tilesM - first_m) : RASTER_GM;
+    const uint32_t r = pid - group * per_group;
+    bm = first_m + r % gsize;
+    bn = r / gsize;
 }
 
 template <int NT> struct TcSmem {
@@ -159,8 +169,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) c64_tf32x3_kernel(const TcArgs 
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const uint32_t tilesM = p.M / TC_BM;
-    const uint32_t bm = blockIdx.x % tilesM, bn = blockIdx.x / tilesM;
+    uint32_t bm, bn;
+    raster(blockIdx.x, p.M / TC_BM, p.N / NT, bm, bn);
     const uint32_t m0 = bm * TC_BM, n0 = bn * NT;
     const uint32_t nkb = (p.K + TC_BK - 1) / TC_BK;
 
@@ -343,7 +353,7 @@ int launch_tc(tnb_ctx* ctx, const TcArgs& a) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int ACC_NT = 128;
 constexpr int ACC_WORKERS = 512;              // warps 0-15
-constexpr int ACC_THREADS = ACC_WORKERS + 64; // + warp 16 (MMA issuer) + warp 17 (bulk-copy issuer)
+constexpr int ACC_THREADS = ACC_WORKERS + 128; // + warpgroup 4: warp 16 MMA issuer, warp 17 bulk-copy issuer, 18-19 idle
 constexpr int ACC_KCB = 8;                    // k-blocks (of 8 complex k) per TMEM chunk
 constexpr int ACC_RAW_STAGES = 6;             // raw (interleaved complex) operand tiles landed by cp.async.bulk
 constexpr int ACC_PL_STAGES = 3;              // split planes consumed by tcgen05.mma
@@ -378,8 +388,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const uint32_t tilesM = p.M / TC_BM;
-    const uint32_t bm = blockIdx.x % tilesM, bn = blockIdx.x / tilesM;
+    uint32_t bm, bn;
+    raster(blockIdx.x, p.M / TC_BM, p.N / ACC_NT, bm, bn);
     const uint32_t m0 = bm * TC_BM, n0 = bn * ACC_NT;
     const uint32_t nkb = p.K / TC_BK;                 // K % 8 == 0 (eligibility)
     const uint32_t nchunks = (nkb + ACC_KCB - 1) / ACC_KCB;
@@ -417,6 +427,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 16) {
+        // registers: launch gives every thread 96; warpgroup 4 shrinks to 40 and the 4 worker warpgroups grow to 104
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ---- worker: raw tile -> split planes, chunk drain, epilogue ----
         const bool feeds_a = tid < 256;
         const int u = feeds_a ? tid : tid - 256;
@@ -493,6 +505,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             *dst = o;
         }
     } else if (warp == 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ---- MMA issuer ----
         if (lane == 0) {
             constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
@@ -533,7 +546,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             }
         }
         __syncwarp();
+    } else if (warp > 17) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle warps: only there to complete warpgroup 4
     } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B ----
         int rs = 0;
         uint32_t rphase = 0;
