@@ -129,6 +129,9 @@ class ContractionPlan:
             for i in t.inds:
                 modes.setdefault(i, len(modes))
         self.modes = modes
+        for i in tuple(sliced) + self.output:
+            if i not in modes:
+                raise ValueError(f"index {i!r} is not carried by any tensor of the network")
         sizes = tn.sizes()
         n = len(tn.tensors)
         self._keep = []
