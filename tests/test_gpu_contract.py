@@ -65,8 +65,8 @@ def test_sliced_equals_unsliced_and_oracle(ctx, dt, tol):
     import tenet_jl_b200 as tb
     tn = tb.workloads.random_regular_network(n=24, bond=3, dtype=dt, seed=5)
     p0 = tb.einexpr(tn, ntrials=4, seed=0)
-    p1 = tb.einexpr(tn, ntrials=4, seed=0, max_log2_size=p0.log2_max_size - 3.2)
-    assert 1 < p1.nslices <= 3 ** 6
+    p1 = tb.einexpr(tn, ntrials=4, seed=0, max_log2_size=p0.log2_max_size - 2.2)
+    assert 1 < p1.nslices <= 3 ** 8
     full = tb.contract(tn, path=p0).item()
     sliced = tb.contract(tn, path=p1).item()
     arrays, inds = _arrays(tn)
@@ -190,7 +190,7 @@ def test_error_paths(ctx):
     # an open index left out of `output` is summed out (einsum semantics), not an error
     r = tb.contract(tn, path=tb.ContractionPath([(0, 1)]), output=("a",))
     assert np.allclose(r.parent, np.full(2, 6.0))
-    with pytest.raises((tb.TnbError, KeyError)):
+    with pytest.raises((tb.TnbError, ValueError)):
         tb.contract(tn, path=tb.ContractionPath([(0, 1)]), output=("a", "zz"))  # output index nobody carries
     with pytest.raises(tb.TnbError):
         tb.contract(tn, path=tb.ContractionPath([(0, 2)]))                      # id does not exist
