@@ -104,7 +104,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(tb, tn, path, budget_macs_log2=37.0):
+def cpu_sample(tb, tn, path, budget_macs_log2=39.5):
     """A bounded CPU sample of the same workload: slice further until one sub-slice is ~2^budget MACs, then time
     the oracle on sub-slice 0.  Returns (flops, seconds, description)."""
     from oracle import einsum_oracle as orc
