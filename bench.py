@@ -32,6 +32,8 @@ WORKLOADS = {
     "sycamore53_m14": "Sycamore-like 53-qubit depth-14 random-circuit amplitude, complex64, sliced (BASELINE configs[2])",
     "sycamore53_m10": "Sycamore-like 53-qubit depth-10 random-circuit amplitude, complex64, sliced",
     "regular3_n60_d4": "random 3-regular network, 60 tensors, bond 4, complex64 (BASELINE configs[1] scaled to fit)",
+    "regular3_n100_d4": "random 3-regular network, 100 tensors, bond 4, complex64, 64 slices (BASELINE configs[1]; 200 tensors needs 2^96 MACs)",
+    "peps6x6_d4_boundary": "6x6 PEPS norm, D=4, complex128, row-by-row boundary path, unsliced (BASELINE configs[3])",
     "peps6x6_d4": "6x6 PEPS norm, D=4, complex128 (BASELINE configs[3])",
     "mps_norm": "MPS <psi|psi>, 32 sites chi=128, complex128, zipper path (BASELINE configs[0])",
     "mps_mpo": "MPS-MPO <psi|H|psi>, 100 sites chi=1024, complex128, env sweep (BASELINE configs[4])",
@@ -41,7 +43,10 @@ WORKLOADS = {
 def build_workload(tb, name):
     """-> (TensorNetwork, ContractionPath, dtype)"""
     from tools.make_paths import network  # noqa
-    if name in ("sycamore53_m14", "sycamore53_m10", "regular3_n60_d4", "peps6x6_d4"):
+    if name == "peps6x6_d4_boundary":
+        tn, _ = tb.workloads.peps_norm_network(6, 6, D=4, p=2, dtype=np.complex128, seed=4)
+        return tn, tb.workloads.peps_boundary_path(6, 6)
+    if name in ("sycamore53_m14", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
         tn = network(name)
         fn = os.path.join(ROOT, "bench_paths", name + ".json")
         if not os.path.exists(fn):

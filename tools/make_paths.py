@@ -23,8 +23,9 @@ def network(name):
     if name == "sycamore53_m10":
         tn, _ = tb.workloads.sycamore_amplitude_network(rows=9, cols=6, cycles=10, seed=53, dtype=np.complex64)
         return tn
-    if name == "regular3_n60_d4":
-        return tb.workloads.random_regular_network(n=60, bond=4, dtype=np.complex64, seed=0)
+    if name.startswith("regular3_n") and name.endswith("_d4"):
+        n = int(name[len("regular3_n"):-len("_d4")])
+        return tb.workloads.random_regular_network(n=n, bond=4, dtype=np.complex64, seed=0)
     if name == "peps6x6_d4":
         return tb.workloads.peps_norm_network(6, 6, D=4, p=2, dtype=np.complex128, seed=4)[0]
     raise SystemExit(f"unknown workload {name}")
