@@ -91,6 +91,16 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
             }
         }
     }
+    if (!force_generic && dtype == TNB_C128 && S.M * S.N >= 1024 && S.K >= 4 &&
+        (double)S.M * (double)S.N * (double)S.K >= (double)(1ll << 16)) {
+        // FP64 tensor-core tile kernel (128 x 64 tile): put the longer free group on the 128 side
+        S.kernel = TNB_KERNEL_C128_DMMA;
+        S.tc_swap = S.N > S.M;
+        const int64_t m = S.tc_swap ? S.N : S.M, n = S.tc_swap ? S.M : S.N;
+        S.splitk = tnb_choose_splitk_dmma(ctx, m, n, S.K, S.L, &kchunk, &ws_elems);
+        S.kchunk = kchunk;
+        return ws_elems;
+    }
     S.splitk = tnb_choose_splitk(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
     S.kchunk = kchunk;
     if (S.splitk > 1) S.kernel = TNB_KERNEL_SPLITK;
@@ -112,6 +122,20 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
             std::swap(lda, ldb);
         }
         return tnb_launch_c64_tc(ctx, a, S.tc_nt, lda, ldb, ctx->c64_mode != TNB_C64_TF32X3_FAST);
+    }
+    if (S.kernel == TNB_KERNEL_C128_DMMA) {
+        if (S.tc_swap) {   // C^T = B * A^T
+            std::swap(a.A, a.B); std::swap(a.M, a.N); std::swap(a.conjA, a.conjB);
+            std::swap(a.am, a.bn); std::swap(a.ak, a.bk); std::swap(a.al, a.bl); std::swap(a.cm, a.cn);
+            std::swap(a.a_kfast, a.b_kfast);
+        }
+        if (S.splitk > 1 && ws) {
+            a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;
+            int rc = tnb_launch_c128_dmma(ctx, a);
+            if (rc) return rc;
+            return tnb_launch_splitk_reduce(ctx, dtype, a);
+        }
+        return tnb_launch_c128_dmma(ctx, a);
     }
     if (S.kernel == TNB_KERNEL_STREAM && ws) {
         a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;

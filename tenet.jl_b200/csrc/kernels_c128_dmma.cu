@@ -1,0 +1,241 @@
+// kernels_c128_dmma.cu — ComplexF64 steps on the FP64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA).
+//
+// What it replaces: the BLAS zgemm behind Muscle.binary_einsum for ComplexF64 networks — MPS/MPO environments
+// (/root/reference/src/Algorithms/DMRG.jl:10-18,106-115), overlaps (src/Operations/overlap.jl:36-50), PEPS norms.
+// tcgen05 has no FP64 kind, so FP64 goes through the warp-level DMMA instruction with accumulators in registers.
+//
+//   C[l,m,n] = alpha * sum_k A[l,m,k] * B[l,n,k] + beta * C      (same table-driven addressing as the generic kernel:
+//   any rank / strides / batch / conj, ragged edges by predication, split-K partials to a workspace)
+//
+// Complex from real DMMAs:  Cre += Are.Bre + (-Aim).Bim ;  Cim += Are.Bim + Aim.Bre  (4 DMMAs per 8x8x4 complex block).
+// CTA tile 128(m) x 64(n) x 8(k), 256 threads = 8 warps as 4(m) x 2(n), warp tile 32 x 32 complex = 64 accumulator
+// registers per thread.  Operands are staged global -> registers -> shared as PLANAR re/im planes [k][m] with a row
+// pitch of (tile+8) doubles: the DMMA fragment loads (lane -> row l/4, k l%4) then hit each bank pair exactly twice,
+// which is the 2-wavefront minimum of a 64-bit warp load.  Per k4 step a warp issues 16 LDS.64 for 64 DMMAs
+// (0.375 B of shared traffic per FMA, 5x less than the 4x4 SIMT micro-tile of the generic kernel).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tnb_internal.h"
+
+namespace {
+
+constexpr int ZT_M = 128, ZT_N = 64, ZT_K = 8, ZT_THREADS = 256;
+constexpr int ZP_A = ZT_M + 8, ZP_B = ZT_N + 8;   // row pitch in doubles (== 16 mod 32 words)
+
+__device__ __forceinline__ int64_t ztab(const TabRef& t, uint32_t i) {
+    uint32_t q = i / t.lo_size;
+    uint32_t r = i - q * t.lo_size;
+    return t.hi[q] + t.lo[r];
+}
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(ZT_THREADS) einsum_c128_dmma_kernel(const EinsumArgs p) {
+    __shared__ double As_re[ZT_K][ZP_A], As_im[ZT_K][ZP_A];
+    __shared__ double Bs_re[ZT_K][ZP_B], Bs_im[ZT_K][ZP_B];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tilesM = (uint32_t)((p.M + ZT_M - 1) / ZT_M);
+    const uint32_t tilesN = (uint32_t)((p.N + ZT_N - 1) / ZT_N);
+    uint32_t bid = blockIdx.x;
+    const uint32_t bm = bid % tilesM; bid /= tilesM;
+    const uint32_t bn = bid % tilesN; bid /= tilesN;
+    const uint32_t ks = bid % (uint32_t)p.splitk;
+    const uint32_t l = bid / (uint32_t)p.splitk;
+    const uint32_t m0 = bm * ZT_M, n0 = bn * ZT_N;
+    const uint32_t M = (uint32_t)p.M, N = (uint32_t)p.N, K = (uint32_t)p.K;
+    uint32_t k_begin = 0, k_end = K;
+    if (p.splitk > 1) {
+        k_begin = (uint32_t)(ks * p.kchunk);
+        uint64_t ke = (uint64_t)k_begin + (uint64_t)p.kchunk;
+        k_end = ke < K ? (uint32_t)ke : K;
+        if (k_begin > k_end) k_begin = k_end;
+    }
+    const double2* __restrict__ A = (const double2*)p.A + ztab(p.al, l);
+    const double2* __restrict__ B = (const double2*)p.B + ztab(p.bl, l);
+
+    // loader mapping: A 128x8 = 4 elements per thread, B 64x8 = 2 per thread
+    int a_ml[4], a_kl[4], b_nl[2], b_kl[2];
+    int64_t a_off[4], b_off[2];
+    bool a_ok[4], b_ok[2];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int e = tid + r * ZT_THREADS;
+        if (p.a_kfast) { a_kl[r] = e % ZT_K; a_ml[r] = e / ZT_K; } else { a_ml[r] = e % ZT_M; a_kl[r] = e / ZT_M; }
+        uint32_t m = m0 + a_ml[r];
+        a_ok[r] = m < M;
+        a_off[r] = a_ok[r] ? ztab(p.am, m) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        int e = tid + r * ZT_THREADS;
+        if (p.b_kfast) { b_kl[r] = e % ZT_K; b_nl[r] = e / ZT_K; } else { b_nl[r] = e % ZT_N; b_kl[r] = e / ZT_N; }
+        uint32_t n = n0 + b_nl[r];
+        b_ok[r] = n < N;
+        b_off[r] = b_ok[r] ? ztab(p.bn, n) : 0;
+    }
+    const double sa = p.conjA ? -1.0 : 1.0, sb = p.conjB ? -1.0 : 1.0;
+
+    double2 ra[4], rb[2];
+    auto load_tile = [&](uint32_t k0) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            uint32_t k = k0 + a_kl[r];
+            ra[r] = (a_ok[r] && k < k_end) ? __ldg(A + a_off[r] + ztab(p.ak, k)) : make_double2(0., 0.);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            uint32_t k = k0 + b_kl[r];
+            rb[r] = (b_ok[r] && k < k_end) ? __ldg(B + b_off[r] + ztab(p.bk, k)) : make_double2(0., 0.);
+        }
+    };
+
+    double cre[4][4][2], cim[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { cre[i][j][0] = cre[i][j][1] = 0.; cim[i][j][0] = cim[i][j][1] = 0.; }
+
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within an 8x4 block
+
+    if (k_begin < k_end) load_tile(k_begin);
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += ZT_K) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            As_re[a_kl[r]][a_ml[r]] = ra[r].x;
+            As_im[a_kl[r]][a_ml[r]] = sa * ra[r].y;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            Bs_re[b_kl[r]][b_nl[r]] = rb[r].x;
+            Bs_im[b_kl[r]][b_nl[r]] = sb * rb[r].y;
+        }
+        __syncthreads();
+        if (k0 + ZT_K < k_end) load_tile(k0 + ZT_K);
+#pragma unroll
+        for (int kk = 0; kk < ZT_K; kk += 4) {
+            double are[4], aim[4], naim[4], bre[4], bim[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                are[i] = As_re[kk + fk][wm + i * 8 + fr];
+                aim[i] = As_im[kk + fk][wm + i * 8 + fr];
+                naim[i] = -aim[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                bre[j] = Bs_re[kk + fk][wn + j * 8 + fr];
+                bim[j] = Bs_im[kk + fk][wn + j * 8 + fr];
+            }
+            // four passes of 16 independent DMMAs: an accumulator is touched again only 32 instructions later
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma(cre[i][j][0], cre[i][j][1], naim[i], bim[j]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue: lane holds C[row fr][cols 2*fk, 2*fk+1] of every 8x8 block
+    const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
+    if (p.splitk == 1) {
+        double2* __restrict__ C = (double2*)p.C + ztab(p.cl, l);
+        int64_t cn_off[4][2];
+        bool n_ok[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
+                n_ok[j][c] = n < N;
+                cn_off[j][c] = n_ok[j][c] ? ztab(p.cn, n) : 0;
+            }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t m = m0 + wm + i * 8 + fr;
+            if (m >= M) continue;
+            const int64_t cm_off = ztab(p.cm, m);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (!n_ok[j][c]) continue;
+                    double xr = cre[i][j][c], xi = cim[i][j][c];
+                    double2 v = make_double2(p.alpha[0] * xr - p.alpha[1] * xi, p.alpha[0] * xi + p.alpha[1] * xr);
+                    double2* dst = C + cm_off + cn_off[j][c];
+                    if (has_beta) {
+                        double2 o = *dst;
+                        v.x += p.beta[0] * o.x - p.beta[1] * o.y;
+                        v.y += p.beta[0] * o.y + p.beta[1] * o.x;
+                    }
+                    *dst = v;
+                }
+        }
+    } else {
+        double2* __restrict__ W = (double2*)p.ws;
+        const uint64_t z = (uint64_t)l * (uint64_t)p.splitk + ks;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t m = m0 + wm + i * 8 + fr;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
+                    if (n < N) W[(z * N + n) * M + m] = make_double2(cre[i][j][c], cim[i][j][c]);
+                }
+        }
+    }
+}
+
+}  // namespace
+
+// split-K factor for this tile shape (same policy as the generic kernel)
+int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
+                           int64_t* ws_elems) {
+    *kchunk = K;
+    *ws_elems = 0;
+    int64_t tiles = ((M + ZT_M - 1) / ZT_M) * ((N + ZT_N - 1) / ZT_N) * L;
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    if (tiles >= sms || K < 128) return 1;
+    int64_t want = (2 * sms + tiles - 1) / tiles;
+    int64_t maxs = K / 32;
+    int64_t s = want < maxs ? want : maxs;
+    const int64_t WS_MAX = (int64_t)1 << 24;
+    while (s > 1 && s * M * N * L > WS_MAX) s--;
+    if (s <= 1) return 1;
+    int64_t kc = (K + s - 1) / s;
+    kc = (kc + ZT_K - 1) / ZT_K * ZT_K;
+    s = (K + kc - 1) / kc;
+    if (s <= 1) return 1;
+    *kchunk = kc;
+    *ws_elems = s * M * N * L;
+    return (int)s;
+}
+
+int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
+    int64_t tilesM = (a.M + ZT_M - 1) / ZT_M, tilesN = (a.N + ZT_N - 1) / ZT_N;
+    int64_t blocks = tilesM * tilesN * a.L * a.splitk;
+    if (blocks <= 0) return TNB_OK;
+    if (blocks >= ((int64_t)1 << 31)) return tnb_set_error(ctx, TNB_EUNSUPPORTED, "grid too large (%lld tiles)", (long long)blocks);
+    einsum_c128_dmma_kernel<<<(unsigned)blocks, ZT_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}

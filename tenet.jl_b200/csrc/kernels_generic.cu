@@ -352,9 +352,9 @@ int tnb_choose_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64
     *ws_elems = 0;
     int64_t tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN) * L;
     const int64_t sms = ctx ? ctx->sm_count : 148;
-    if (tiles >= sms || K < 512) return 1;
+    if (tiles >= sms || K < 128) return 1;
     int64_t want = (2 * sms + tiles - 1) / tiles;          // ~2 CTAs per SM
-    int64_t maxs = K / 128;                                 // at least 128 k per split
+    int64_t maxs = K / 32;                                  // at least 32 k per split
     int64_t s = want < maxs ? want : maxs;
     const int64_t WS_MAX = (int64_t)1 << 24;                // elements
     while (s > 1 && s * M * N * L > WS_MAX) s--;

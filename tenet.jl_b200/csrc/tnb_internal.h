@@ -136,6 +136,10 @@ int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);
 
+// kernels_c128_dmma.cu
+int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);
+int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a);
+
 // planner.cpp  (pure host code; also used by the dry-run plan that CPU tests inspect)
 struct PlanTensor {
     std::vector<int32_t> modes;

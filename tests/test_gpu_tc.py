@@ -84,3 +84,30 @@ def test_thin_reduction(ctx, dt, tol, M, N):
         assert ctx.last_kernel == "stream"
         ref = a.astype(np.complex128).T @ b.astype(np.complex128)
         assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 8), (33, 47, 5), (200, 130, 77), (64, 512, 256), (1000, 8, 300), (256, 256, 4096)])
+def test_c128_dmma_matches_oracle(ctx, M, N, K):
+    """FP64 tensor-core kernel: ragged edges, operand swap (N > M), split-K, against c128 numpy (1e-12)."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a, b = crand(rng, (M, K), np.complex128), crand(rng, (K, N), np.complex128)
+    c = tb.binary_einsum(tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("k", "n")))
+    if M * N >= 1024 and M * N * K >= 65536:
+        assert ctx.last_kernel == "c128_dmma"
+    ref = a @ b
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 1e-12
+    c2 = tb.binary_einsum(tb.Tensor(a, ("m", "k")).conj(), tb.Tensor(b.T.copy(), ("n", "k")).conj(), out=("n", "m"))
+    assert np.abs(c2.parent - np.conj(ref).T).max() / np.abs(ref).max() < 1e-12
+
+
+def test_c128_dmma_batch_and_high_rank(ctx):
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(11)
+    a = crand(rng, (3, 4, 5, 16, 7), np.complex128)     # b x y k z
+    b = crand(rng, (16, 3, 8, 9), np.complex128)        # k b u v
+    c = tb.binary_einsum(tb.Tensor(a, "bxykz"), tb.Tensor(b, "kbuv"), dims=("k",))
+    ref = np.einsum("bxykz,kbuv->xyzuvb", a, b)
+    assert c.inds == tuple("xyzuvb")
+    assert ctx.last_kernel == "c128_dmma"
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 1e-12
