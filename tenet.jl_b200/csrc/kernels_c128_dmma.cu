@@ -28,9 +28,13 @@ __device__ __forceinline__ int64_t ztab(const TabRef& t, uint32_t i) {
     return t.hi[q] + t.lo[r];
 }
 
-__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+// D(16x8) += A(16x8) * B(8x8), FP64.  Fragments (g = lane/4, t = lane%4):
+//   a0 (row g, k t)  a1 (row g+8, k t)  a2 (row g, k t+4)  a3 (row g+8, k t+4);  b0 (k t, col g)  b1 (k t+4, col g);
+//   d0 (row g, col 2t)  d1 (row g, col 2t+1)  d2 (row g+8, col 2t)  d3 (row g+8, col 2t+1)
+__device__ __forceinline__ void dmma16(double (&d)[4], const double (&a)[4], const double (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+        : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
 __global__ void __launch_bounds__(ZT_THREADS) einsum_c128_dmma_kernel(const EinsumArgs p) {
@@ -93,14 +97,17 @@ __global__ void __launch_bounds__(ZT_THREADS) einsum_c128_dmma_kernel(const Eins
         }
     };
 
-    double cre[4][4][2], cim[4][4][2];
+    // warp tile 32 x 32 complex = 2 (m16) x 4 (n8) blocks, 4 accumulator doubles per block and part
+    double cre[2][4][4], cim[2][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { cre[i][j][0] = cre[i][j][1] = 0.; cim[i][j][0] = cim[i][j][1] = 0.; }
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { cre[i][j][c] = 0.; cim[i][j][c] = 0.; }
 
     const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
-    const int fr = lane >> 2, fk = lane & 3;     // fragment row / k within an 8x4 block
+    const int fr = lane >> 2, fk = lane & 3;     // fragment row group / k within a block
 
     if (k_begin < k_end) load_tile(k_begin);
     for (uint32_t k0 = k_begin; k0 < k_end; k0 += ZT_K) {
@@ -116,92 +123,88 @@ __global__ void __launch_bounds__(ZT_THREADS) einsum_c128_dmma_kernel(const Eins
         }
         __syncthreads();
         if (k0 + ZT_K < k_end) load_tile(k0 + ZT_K);
+        {
+            double are[2][4], aim[2][4], naim[2][4], bre[4][2], bim[4][2];
 #pragma unroll
-        for (int kk = 0; kk < ZT_K; kk += 4) {
-            double are[4], aim[4], naim[4], bre[4], bim[4];
+            for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                are[i] = As_re[kk + fk][wm + i * 8 + fr];
-                aim[i] = As_im[kk + fk][wm + i * 8 + fr];
-                naim[i] = -aim[i];
-            }
+                for (int c = 0; c < 4; c++) {
+                    const int row = wm + i * 16 + fr + (c & 1) * 8, k = fk + (c >> 1) * 4;
+                    are[i][c] = As_re[k][row];
+                    aim[i][c] = As_im[k][row];
+                    naim[i][c] = -aim[i][c];
+                }
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                bre[j] = Bs_re[kk + fk][wn + j * 8 + fr];
-                bim[j] = Bs_im[kk + fk][wn + j * 8 + fr];
-            }
-            // four passes of 16 independent DMMAs: an accumulator is touched again only 32 instructions later
+            for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int c = 0; c < 2; c++) {
+                    bre[j][c] = Bs_re[fk + c * 4][wn + j * 8 + fr];
+                    bim[j][c] = Bs_im[fk + c * 4][wn + j * 8 + fr];
+                }
+            // four passes of 8 independent MMAs: an accumulator is touched again only 16 instructions later
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+            for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) dmma16(cre[i][j], are[i], bre[j]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+            for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) dmma16(cim[i][j], are[i], bim[j]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(cre[i][j][0], cre[i][j][1], naim[i], bim[j]);
+            for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) dmma16(cre[i][j], naim[i], bim[j]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma16(cim[i][j], aim[i], bre[j]);
         }
         __syncthreads();
     }
 
-    // epilogue: lane holds C[row fr][cols 2*fk, 2*fk+1] of every 8x8 block
+    // epilogue: lane holds rows fr, fr+8 and columns 2*fk, 2*fk+1 of every 16x8 block
     const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
-    if (p.splitk == 1) {
-        double2* __restrict__ C = (double2*)p.C + ztab(p.cl, l);
-        int64_t cn_off[4][2];
-        bool n_ok[4][2];
+    double2* __restrict__ C = (double2*)p.C + (p.splitk == 1 ? ztab(p.cl, l) : 0);
+    double2* __restrict__ W = (double2*)p.ws;
+    const uint64_t z = (uint64_t)l * (uint64_t)p.splitk + ks;
+    int64_t cn_off[4][2];
+    bool n_ok[4][2];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
-                n_ok[j][c] = n < N;
-                cn_off[j][c] = n_ok[j][c] ? ztab(p.cn, n) : 0;
-            }
+        for (int c = 0; c < 2; c++) {
+            uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
+            n_ok[j][c] = n < N;
+            cn_off[j][c] = (n_ok[j][c] && p.splitk == 1) ? ztab(p.cn, n) : 0;
+        }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t m = m0 + wm + i * 8 + fr;
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t m = m0 + wm + i * 16 + fr + h * 8;
             if (m >= M) continue;
-            const int64_t cm_off = ztab(p.cm, m);
+            const int64_t cm_off = p.splitk == 1 ? ztab(p.cm, m) : 0;
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
                 for (int c = 0; c < 2; c++) {
                     if (!n_ok[j][c]) continue;
-                    double xr = cre[i][j][c], xi = cim[i][j][c];
-                    double2 v = make_double2(p.alpha[0] * xr - p.alpha[1] * xi, p.alpha[0] * xi + p.alpha[1] * xr);
-                    double2* dst = C + cm_off + cn_off[j][c];
-                    if (has_beta) {
-                        double2 o = *dst;
-                        v.x += p.beta[0] * o.x - p.beta[1] * o.y;
-                        v.y += p.beta[0] * o.y + p.beta[1] * o.x;
+                    const double xr = cre[i][j][h * 2 + c], xi = cim[i][j][h * 2 + c];
+                    if (p.splitk == 1) {
+                        double2 v = make_double2(p.alpha[0] * xr - p.alpha[1] * xi, p.alpha[0] * xi + p.alpha[1] * xr);
+                        double2* dst = C + cm_off + cn_off[j][c];
+                        if (has_beta) {
+                            double2 o = *dst;
+                            v.x += p.beta[0] * o.x - p.beta[1] * o.y;
+                            v.y += p.beta[0] * o.y + p.beta[1] * o.x;
+                        }
+                        *dst = v;
+                    } else {
+                        uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
+                        W[(z * N + n) * M + m] = make_double2(xr, xi);
                     }
-                    *dst = v;
                 }
         }
-    } else {
-        double2* __restrict__ W = (double2*)p.ws;
-        const uint64_t z = (uint64_t)l * (uint64_t)p.splitk + ks;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            uint32_t m = m0 + wm + i * 8 + fr;
-            if (m >= M) continue;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    uint32_t n = n0 + wn + j * 8 + 2 * fk + c;
-                    if (n < N) W[(z * N + n) * M + m] = make_double2(cre[i][j][c], cim[i][j][c]);
-                }
-        }
-    }
 }
 
 }  // namespace
