@@ -83,11 +83,15 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
         if (tc_ok) {
             int nt = tnb_tc_c64_tile(S.M, S.N, S.K, S.L, S.a_mmajor, S.b_nmajor);
             int nt_sw = tnb_tc_c64_tile(S.N, S.M, S.K, S.L, S.b_nmajor, S.a_mmajor);
-            if (nt || nt_sw) {
+            const int64_t lda = S.K > 1 ? S.ak.stride : S.M, ldb = S.K > 1 ? S.bk.stride : S.N;
+            if ((nt || nt_sw) && lda % 2 == 0 && ldb % 2 == 0) {
                 S.kernel = TNB_KERNEL_C64_TF32;
-                S.tc_swap = nt_sw > nt;
+                S.tc_swap = nt_sw > nt || (nt_sw == nt && S.N > S.M);   // longer free group on the 128-row side
                 S.tc_nt = S.tc_swap ? nt_sw : nt;
-                return 0;
+                const int64_t m = S.tc_swap ? S.N : S.M, n = S.tc_swap ? S.M : S.N;
+                S.splitk = tnb_tc_c64_splitk(ctx, m, n, S.K, &kchunk, &ws_elems);
+                S.kchunk = kchunk;                                       // in k-blocks of 8 for this kernel
+                return ws_elems;
             }
         }
     }
@@ -121,7 +125,16 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
             std::swap(a.A, a.B); std::swap(a.M, a.N); std::swap(a.cm, a.cn); std::swap(a.conjA, a.conjB);
             std::swap(lda, ldb);
         }
-        return tnb_launch_c64_tc(ctx, a, S.tc_nt, lda, ldb, ctx->c64_mode != TNB_C64_TF32X3_FAST);
+        if (S.splitk > 1 && ws) { a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws; }
+        int rc = tnb_launch_c64_tc(ctx, a, S.tc_nt, lda, ldb, ctx->c64_mode != TNB_C64_TF32X3_FAST);
+        if (rc == TNB_OK && a.splitk > 1) return tnb_launch_splitk_reduce(ctx, dtype, a);
+        if (rc != -1) return rc;
+        // operands not 16-byte aligned for the bulk copies (odd leaf offset): exact-FP32 generic kernel instead
+        EinsumArgs g;
+        fill_args(S, dev_blob, &g);
+        g.A = A; g.B = B; g.C = C;
+        g.alpha[0] = alpha[0]; g.alpha[1] = alpha[1]; g.beta[0] = beta[0]; g.beta[1] = beta[1];
+        return tnb_launch_einsum_generic(ctx, dtype, g);
     }
     if (S.kernel == TNB_KERNEL_C128_DMMA) {
         if (S.tc_swap) {   // C^T = B * A^T

@@ -139,6 +139,10 @@ struct TcArgs {
     TabRef cm, cn;
     int32_t conjA, conjB;
     float alpha[2], beta[2];
+    // split-K (chunked kernel only): CTA z handles k-blocks [z*kb_per_split, ...) and writes raw partials to
+    // ws[(z*N + n)*M + m]; the deterministic reducer of kernels_generic.cu finishes the job
+    float2* ws;
+    uint32_t splitk, kb_per_split;
 };
 
 __device__ __forceinline__ int64_t tabc(const TabRef& t, uint32_t i) {
@@ -388,10 +392,17 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t tilesM = (p.M + TC_BM - 1) / TC_BM, tilesN = (p.N + ACC_NT - 1) / ACC_NT;
+    const uint32_t ntiles = tilesM * tilesN;
+    const uint32_t zsplit = blockIdx.x / ntiles;
     uint32_t bm, bn;
-    raster(blockIdx.x, p.M / TC_BM, p.N / ACC_NT, bm, bn);
+    raster(blockIdx.x - zsplit * ntiles, tilesM, tilesN, bm, bn);
     const uint32_t m0 = bm * TC_BM, n0 = bn * ACC_NT;
-    const uint32_t nkb = p.K / TC_BK;                 // K % 8 == 0 (eligibility)
+    const uint32_t mv = (p.M - m0) < TC_BM ? (p.M - m0) : TC_BM;      // valid rows / columns of a ragged edge tile
+    const uint32_t nv = (p.N - n0) < ACC_NT ? (p.N - n0) : ACC_NT;
+    const uint32_t nkb_total = (p.K + TC_BK - 1) / TC_BK;
+    const uint32_t kb0 = zsplit * p.kb_per_split;
+    const uint32_t nkb = (nkb_total - kb0) < p.kb_per_split ? (nkb_total - kb0) : p.kb_per_split;
     const uint32_t nchunks = (nkb + ACC_KCB - 1) / ACC_KCB;
 
     const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
@@ -420,15 +431,16 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
-    for (int i = tid; i < ACC_NT; i += ACC_THREADS) cn_tab[i] = tabc(p.cn, n0 + i);
+    if (p.splitk == 1)
+        for (int i = tid; i < (int)nv; i += ACC_THREADS) cn_tab[i] = tabc(p.cn, n0 + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 16) {
-        // registers: launch gives every thread 96; warpgroup 4 shrinks to 40 and the 4 worker warpgroups grow to 104
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // registers: launch gives every thread 96; warpgroup 4 shrinks to 32 and the 4 worker warpgroups grow to 112
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ---- worker: raw tile -> split planes, chunk drain, epilogue ----
         const bool feeds_a = tid < 256;
         const int u = feeds_a ? tid : tid - 256;
@@ -437,6 +449,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         const int plane_bytes = feeds_a ? S::A_PLANE : S::B_PLANE;
         const int plane_base = feeds_a ? 0 : 4 * S::A_PLANE;
         const int raw_base = S::RAW_OFF + (feeds_a ? 0 : S::RAW_HALF) + (pkc * 4 * TC_BM + prow) * 8;
+        const bool row_ok = (uint32_t)prow < (feeds_a ? mv : nv);
         const int q = warp & 3, g = warp >> 2;        // TMEM lane quarter, 32-column group
         float tr[32], ti[32];
 #pragma unroll
@@ -473,8 +486,12 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             mbar_wait(raw_full(rs), rphase);
             float2 v[4];
             const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+            const uint32_t kleft = p.K - (kb0 + kb) * TC_BK;      // >= 8 except in the last k-block of a ragged K
 #pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+            for (int i = 0; i < 4; i++) {
+                v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v[i] = make_float2(0.f, 0.f);   // stale smem beyond the edge
+            }
             mbar_wait(pl_empty(ps), pphase ^ 1);
             split_store(smem + ps * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v, pconj);
             fence_proxy_async_smem();
@@ -490,22 +507,34 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
 
         // ---- epilogue: totals -> alpha/beta -> scatter ----
         const uint32_t row = q * 32 + lane;
-        float2* __restrict__ Crow = p.C + tabc(p.cm, m0 + row);
-        const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
-        const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+        if (row < mv) {
+            if (p.splitk == 1) {
+                float2* __restrict__ Crow = p.C + tabc(p.cm, m0 + row);
+                const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
+                const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
-            float2* dst = Crow + cn_tab[g * 32 + j];
-            if (has_beta) {
-                float2 old = *dst;
-                o.x += br * old.x - bi * old.y;
-                o.y += br * old.y + bi * old.x;
+                for (int j = 0; j < 32; j++) {
+                    if ((uint32_t)(g * 32 + j) >= nv) break;
+                    float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
+                    float2* dst = Crow + cn_tab[g * 32 + j];
+                    if (has_beta) {
+                        float2 old = *dst;
+                        o.x += br * old.x - bi * old.y;
+                        o.y += br * old.y + bi * old.x;
+                    }
+                    *dst = o;
+                }
+            } else {
+                float2* __restrict__ W = p.ws + ((uint64_t)zsplit * p.N + n0) * p.M + (m0 + row);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if ((uint32_t)(g * 32 + j) >= nv) break;
+                    W[(uint64_t)(g * 32 + j) * p.M] = make_float2(tr[j], ti[j]);
+                }
             }
-            *dst = o;
         }
     } else if (warp == 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ---- MMA issuer ----
         if (lane == 0) {
             constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
@@ -547,9 +576,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         }
         __syncwarp();
     } else if (warp > 17) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // idle warps: only there to complete warpgroup 4
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // idle warps: only there to complete warpgroup 4
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B ----
         int rs = 0;
         uint32_t rphase = 0;
@@ -557,13 +586,16 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         const int krow = lane & 7;
         const float2* src = is_a ? p.A + m0 : p.B + n0;
         const int64_t ld = is_a ? p.lda : p.ldb;
+        const uint32_t row_bytes = (is_a ? mv : nv) * 8;          // multiple of 16: M, N even (eligibility)
         for (uint32_t kb = 0; kb < nkb; kb++) {
+            const uint32_t k0 = (kb0 + kb) * TC_BK;
+            const uint32_t kv = (p.K - k0) < TC_BK ? (p.K - k0) : TC_BK;
             mbar_wait(raw_empty(rs), rphase ^ 1);
-            if (lane == 0) mbar_expect_tx(raw_full(rs), S::RAW_STAGE);
+            if (lane == 0) mbar_expect_tx(raw_full(rs), kv * (mv + nv) * 8);
             __syncwarp();
-            if (lane < 16) {
+            if (lane < 16 && (uint32_t)krow < kv) {
                 const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (is_a ? 0 : S::RAW_HALF) + krow * TC_BM * 8);
-                bulk_g2s(dst, src + (int64_t)(kb * TC_BK + krow) * ld, TC_BM * 8, raw_full(rs));
+                bulk_g2s(dst, src + (int64_t)(k0 + krow) * ld, row_bytes, raw_full(rs));
             }
             if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
         }
@@ -582,33 +614,55 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
         TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AccSmem::TOTAL));
         configured[ctx->device & 15] = true;
     }
-    const unsigned grid = (a.M / TC_BM) * (a.N / ACC_NT);
+    const unsigned grid = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + ACC_NT - 1) / ACC_NT) * a.splitk;
     c64_tf32x3_acc_kernel<<<grid, ACC_THREADS, AccSmem::TOTAL, ctx->stream>>>(a);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
 }
 
-// cp.async.bulk needs 16-byte aligned rows: even leading dimensions, 16-byte aligned bases, K a multiple of 8
+// cp.async.bulk needs 16-byte aligned rows: even M, N and leading dimensions, 16-byte aligned bases
 bool tc_acc_ok(const TcArgs& a) {
-    return a.N % ACC_NT == 0 && a.K % TC_BK == 0 && (a.lda % 2) == 0 && (a.ldb % 2) == 0 &&
+    return (a.M % 2) == 0 && (a.N % 2) == 0 && (a.lda % 2) == 0 && (a.ldb % 2) == 0 &&
            ((uintptr_t)a.A % 16) == 0 && ((uintptr_t)a.B % 16) == 0;
 }
 
-
 }  // namespace
 
-// Eligibility: complex64, no batch, both operands dense with the free index fastest, tile-aligned sizes.
-// Returns the N tile (256/128/64) or 0.
+// Plan-time eligibility of the tcgen05 kernels: complex64, no batch, both operands dense with the free index fastest.
+// Returns the tile class: 256 / 128 = aligned to the fast kernel's tiles as well, 1 = chunked kernel only (ragged), 0 = no.
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor) {
     if (L != 1 || !a_mmajor || !b_nmajor) return 0;
-    if (M % TC_BM != 0 || K < 16) return 0;
-    if (M / TC_BM >= (1 << 20)) return 0;
-    if (N % 256 == 0) return 256;
-    if (N % 128 == 0) return 128;
-    return 0;
+    if (K < 16 || (M % 2) || (N % 2) || M < 32 || N < 32) return 0;
+    if (M >= ((int64_t)1 << 27) || N >= ((int64_t)1 << 27)) return 0;
+    if (M % TC_BM == 0 && N % 256 == 0) return 256;
+    if (M % TC_BM == 0 && N % 128 == 0) return 128;
+    return 1;
 }
 
+// split-K for the chunked kernel: few output tiles, long K.  Returns the split count; kb_per_split in k-blocks of 8.
+int tnb_tc_c64_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t* kb_per_split, int64_t* ws_elems) {
+    const int64_t nkb = (K + TC_BK - 1) / TC_BK;
+    *kb_per_split = nkb;
+    *ws_elems = 0;
+    const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + ACC_NT - 1) / ACC_NT);
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    if (tiles * 2 > sms || nkb < 4 * ACC_KCB) return 1;
+    int64_t s = (2 * sms) / tiles;
+    const int64_t maxs = nkb / (2 * ACC_KCB);                 // at least 128 k per split
+    if (s > maxs) s = maxs;
+    while (s > 1 && s * M * N > ((int64_t)1 << 25)) s--;
+    if (s <= 1) return 1;
+    int64_t per = (nkb + s - 1) / s;
+    per = (per + ACC_KCB - 1) / ACC_KCB * ACC_KCB;
+    s = (nkb + per - 1) / per;
+    if (s <= 1) return 1;
+    *kb_per_split = per;
+    *ws_elems = s * M * N;
+    return (int)s;
+}
+
+// returns TNB_OK, or -1 if the operands are not 16-byte aligned for the bulk copies (caller falls back)
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked) {
     TcArgs a;
     a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
@@ -618,8 +672,13 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
     a.conjA = e.conjA; a.conjB = e.conjB;
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
-    if (chunked && tc_acc_ok(a)) return launch_tc_acc(ctx, a);
-    if (nt == 256) return launch_tc<256>(ctx, a);
-    if (nt == 128) return launch_tc<128>(ctx, a);
-    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "no tcgen05 tile for N tile %d", nt);
+    a.ws = (float2*)e.ws;
+    a.splitk = e.splitk > 1 ? (uint32_t)e.splitk : 1u;
+    a.kb_per_split = e.splitk > 1 ? (uint32_t)e.kchunk : (uint32_t)((e.K + TC_BK - 1) / TC_BK);
+    if (!chunked && a.splitk == 1 && nt >= 128) {
+        if (nt == 256) return launch_tc<256>(ctx, a);
+        return launch_tc<128>(ctx, a);
+    }
+    if (!tc_acc_ok(a)) return -1;
+    return launch_tc_acc(ctx, a);
 }

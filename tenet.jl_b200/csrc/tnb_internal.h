@@ -135,6 +135,7 @@ int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
 // kernels_c64_tc.cu
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);
+int tnb_tc_c64_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t* kb_per_split, int64_t* ws_elems);
 
 // kernels_c128_dmma.cu
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);

@@ -13,7 +13,8 @@ def crand(rng, shape, dt=np.complex64):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 40), (128, 128, 16), (384, 512, 200), (512, 512, 1024),
-                                   (256, 1024, 8192)])
+                                   (256, 1024, 8192),
+                                   (200, 130, 77), (1000, 34, 300), (64, 4096, 16384), (130, 258, 2050)])  # ragged / split-K
 def test_tc_matches_oracle(ctx, M, N, K):
     import tenet_jl_b200 as tb
     rng = np.random.default_rng(M + N + K)
@@ -111,3 +112,18 @@ def test_c128_dmma_batch_and_high_rank(ctx):
     assert c.inds == tuple("xyzuvb")
     assert ctx.last_kernel == "c128_dmma"
     assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_tc_misaligned_view_falls_back(ctx):
+    """a view whose first element is only 8-byte aligned cannot be bulk-copied: the step runs on the exact-FP32
+    generic kernel instead (same result, no error)."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(21)
+    big = crand(rng, (130, 64))
+    b = crand(rng, (256, 64))
+    t = tb.Tensor(big, ("m", "k"))
+    t.device()
+    v = t.view(("m", slice(1, 129)))
+    c = tb.binary_einsum(v, tb.Tensor(b, ("n", "k")))
+    ref = big[1:129].astype(np.complex128) @ b.astype(np.complex128).T
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 2e-5
