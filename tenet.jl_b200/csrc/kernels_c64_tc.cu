@@ -360,7 +360,7 @@ constexpr int ACC_WORKERS = 512;              // warps 0-15
 constexpr int ACC_THREADS = ACC_WORKERS + 128; // + warpgroup 4: warp 16 MMA issuer, warp 17 bulk-copy issuer, 18-19 idle
 constexpr int ACC_KCB = 8;                    // k-blocks (of 8 complex k) per TMEM chunk
 constexpr int ACC_RAW_STAGES = 6;             // raw (interleaved complex) operand tiles landed by cp.async.bulk
-constexpr int ACC_PL_STAGES = 3;              // split planes consumed by tcgen05.mma
+constexpr int ACC_PL_STAGES = 4;              // split planes consumed by tcgen05.mma (workers fill them two at a time)
 
 struct AccSmem {
     static constexpr int A_PLANE = TC_BM * TC_BK * 4;                  // 4 KB
@@ -476,32 +476,56 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             if (lane == 0) mbar_arrive(accempty_bar(set));
         };
 
+        // Two k-blocks per iteration: one fence.proxy.async + one round of barrier traffic per 16 k, and twice the
+        // independent work in flight per warp (the loop is latency- not issue-bound).  Stage counts are even.
+        static_assert(ACC_RAW_STAGES % 2 == 0 && ACC_PL_STAGES % 2 == 0 && ACC_KCB % 2 == 0, "pairs of k-blocks");
         int rs = 0, ps = 0;
         uint32_t rphase = 0, pphase = 0, drained = 0;
-        for (uint32_t kb = 0; kb < nkb; kb++) {
+        for (uint32_t kb = 0; kb < nkb; kb += 2) {
             if (kb % ACC_KCB == 0) {
                 const uint32_t c = kb / ACC_KCB;
                 while (drained + 2 <= c) { drain(drained); drained++; }
             }
+            const bool two = kb + 1 < nkb;
+            float2 v0[4], v1[4];
             mbar_wait(raw_full(rs), rphase);
-            float2 v[4];
-            const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
-            const uint32_t kleft = p.K - (kb0 + kb) * TC_BK;      // >= 8 except in the last k-block of a ragged K
+            {
+                const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+                const uint32_t kleft = p.K - (kb0 + kb) * TC_BK;      // >= 8 except in the last k-block of a ragged K
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
-                if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v[i] = make_float2(0.f, 0.f);   // stale smem beyond the edge
+                for (int i = 0; i < 4; i++) {
+                    v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                    if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v0[i] = make_float2(0.f, 0.f);   // stale smem beyond the edge
+                }
+            }
+            if (two) {
+                mbar_wait(raw_full(rs + 1), rphase);
+                const uint8_t* raw = smem + (rs + 1) * S::RAW_STAGE + raw_base;
+                const uint32_t kleft = p.K - (kb0 + kb + 1) * TC_BK;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    v1[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                    if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v1[i] = make_float2(0.f, 0.f);
+                }
             }
             mbar_wait(pl_empty(ps), pphase ^ 1);
-            split_store(smem + ps * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v, pconj);
+            split_store(smem + ps * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v0, pconj);
+            if (two) {
+                mbar_wait(pl_empty(ps + 1), pphase ^ 1);
+                split_store(smem + (ps + 1) * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v1, pconj);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(pl_full(ps));
                 mbar_arrive(raw_empty(rs));
+                if (two) {
+                    mbar_arrive(pl_full(ps + 1));
+                    mbar_arrive(raw_empty(rs + 1));
+                }
             }
-            if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
-            if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
+            rs += 2; if (rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
+            ps += 2; if (ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
         }
         while (drained < nchunks) { drain(drained); drained++; }
 
