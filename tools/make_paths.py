@@ -38,13 +38,22 @@ def main():
     ap.add_argument("--target", type=float, default=27.0, help="log2 of the largest intermediate (elements)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--minimize", default="flops")
+    ap.add_argument("--method", default="hyper", choices=["hyper", "greedy"])
+    ap.add_argument("--keep", type=int, default=8)
+    ap.add_argument("--reconf-size", type=int, default=9)
+    ap.add_argument("--out", default="")
     a = ap.parse_args()
     tn = network(a.name)
     inputs = [t.inds for t in tn.tensors]
     sizes = tn.sizes()
     t0 = time.time()
-    p = tb.pathfinder.search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
-                             minimize=a.minimize)
+    if a.method == "hyper":
+        from tenet_jl_b200 import treeopt
+        p = treeopt.hyper_search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
+                                 reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True)
+    else:
+        p = tb.pathfinder.search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
+                                 minimize=a.minimize)
     dt = time.time() - t0
     lab = {i: k for k, i in enumerate(tn.inds("all"))}
     out = {"workload": a.name, "ntensors": len(inputs), "steps": [list(s) for s in p.steps],
@@ -52,7 +61,7 @@ def main():
            "log2_max_size": p.log2_max_size, "nslices_log2": float(np.log2(p.nslices)),
            "search": {"trials": a.trials, "seed": a.seed, "seconds": round(dt, 1), **p.info}}
     os.makedirs(os.path.join(ROOT, "bench_paths"), exist_ok=True)
-    fn = os.path.join(ROOT, "bench_paths", a.name + ".json")
+    fn = a.out or os.path.join(ROOT, "bench_paths", a.name + ".json")
     with open(fn, "w") as f:
         json.dump(out, f)
     print(f"{fn}: per-slice 2^{p.log2_macs:.2f} MACs, peak 2^{p.log2_max_size:.1f} elems, 2^{np.log2(p.nslices):.0f} slices, "
