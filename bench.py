@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (description, dtype)
     "sycamore53_m14": "Sycamore-like 53-qubit depth-14 random-circuit amplitude, complex64, sliced (BASELINE configs[2])",
+    "sycamore53_m14_greedy": "same network, round-1 first-light path (plain greedy, 2^63 MACs total): two 16384x8192x8192 GEMMs dominate",
     "sycamore53_m10": "Sycamore-like 53-qubit depth-10 random-circuit amplitude, complex64, sliced",
     "regular3_n60_d4": "random 3-regular network, 60 tensors, bond 4, complex64 (BASELINE configs[1] scaled to fit)",
     "regular3_n100_d4": "random 3-regular network, 100 tensors, bond 4, complex64, 64 slices (BASELINE configs[1]; 200 tensors needs 2^96 MACs)",
@@ -46,7 +47,7 @@ def build_workload(tb, name):
     if name == "peps6x6_d4_boundary":
         tn, _ = tb.workloads.peps_norm_network(6, 6, D=4, p=2, dtype=np.complex128, seed=4)
         return tn, tb.workloads.peps_boundary_path(6, 6)
-    if name in ("sycamore53_m14", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
+    if name in ("sycamore53_m14", "sycamore53_m14_greedy", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
         tn = network(name)
         fn = os.path.join(ROOT, "bench_paths", name + ".json")
         if not os.path.exists(fn):

@@ -250,7 +250,44 @@ __global__ void __launch_bounds__(THIN_THREADS) einsum_thin_kernel(const EinsumA
     const uint32_t k_begin = kb < K ? (uint32_t)kb : K;
     const uint32_t k_end = ke64 < K ? (uint32_t)ke64 : K;
     const bool aff = p.ak.affine && p.bk.affine;
-    for (uint32_t k0 = k_begin + threadIdx.x; k0 < k_end; k0 += THIN_THREADS * THIN_UNROLL) {
+    uint32_t k_scalar = k_begin;
+    // Fast path for the amplitude-closing dot product (M = N = 1, both operands contiguous in k): 32-byte loads
+    // (4 complex64 / 2 complex128 per lane and instruction), 4 loads of each operand in flight per thread.
+    if (M == 1 && N == 1 && aff && p.ak.stride == 1 && p.bk.stride == 1 &&
+        (((uintptr_t)(A + am[0] + k_begin) | (uintptr_t)(B + bn[0] + k_begin)) & 31) == 0) {
+        constexpr int VEC = 32 / (int)sizeof(E);
+        struct __align__(32) Pack { E v[VEC]; };
+        const Pack* __restrict__ Av = reinterpret_cast<const Pack*>(A + am[0] + k_begin);
+        const Pack* __restrict__ Bv = reinterpret_cast<const Pack*>(B + bn[0] + k_begin);
+        const uint32_t nvec = (k_end - k_begin) / VEC;
+        E s0 = ezero((E*)0), s1 = ezero((E*)0);
+        uint32_t i = threadIdx.x;
+        for (; i + 3 * THIN_THREADS < nvec; i += 4 * THIN_THREADS) {
+            Pack pa[4], pb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { pa[u] = Av[i + u * THIN_THREADS]; pb[u] = Bv[i + u * THIN_THREADS]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    E av = p.conjA ? econj(pa[u].v[e]) : pa[u].v[e];
+                    E bv = p.conjB ? econj(pb[u].v[e]) : pb[u].v[e];
+                    emac((e & 1) ? s1 : s0, av, bv);
+                }
+        }
+        for (; i < nvec; i += THIN_THREADS) {
+            Pack pa = Av[i], pb = Bv[i];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                E av = p.conjA ? econj(pa.v[e]) : pa.v[e];
+                E bv = p.conjB ? econj(pb.v[e]) : pb.v[e];
+                emac((e & 1) ? s1 : s0, av, bv);
+            }
+        }
+        acc[0][0] = eadd(s0, s1);
+        k_scalar = k_begin + nvec * VEC;          // ragged tail handled by the generic loop below
+    }
+    for (uint32_t k0 = k_scalar + threadIdx.x; k0 < k_end; k0 += THIN_THREADS * THIN_UNROLL) {
         E a[THIN_UNROLL][THIN_MAX], b[THIN_UNROLL][THIN_MAX];
 #pragma unroll
         for (int u = 0; u < THIN_UNROLL; u++) {
