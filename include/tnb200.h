@@ -161,6 +161,7 @@ typedef struct tnb_step_info {
 #define TNB_KERNEL_C128_DMMA 2    /* mma.sync f64 tensor-core kernel                         */
 #define TNB_KERNEL_STREAM    3    /* memory-bound streaming kernel (small K*N)               */
 #define TNB_KERNEL_SPLITK    4    /* split-K reduction (M*N tiny, K huge)                    */
+#define TNB_KERNEL_STEM      5    /* HBM-bound streaming kernel: huge dense operand x tiny operand */
 int tnb_plan_get_step(const tnb_plan* plan, int32_t step, tnb_step_info* info);
 
 /* per-step device timing (CUDA events on the context stream; one host sync per slice while enabled) */

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["csrc/context.cu", "csrc/api.cu", "csrc/comm.cu", "csrc/kernels_generic.cu", "csrc/kernels_c64_tc.cu", "csrc/kernels_c128_dmma.cu", "csrc/planner.cpp"]
+SRC = ["csrc/context.cu", "csrc/api.cu", "csrc/comm.cu", "csrc/kernels_generic.cu", "csrc/kernels_c64_tc.cu", "csrc/kernels_c128_dmma.cu", "csrc/kernels_stem.cu", "csrc/planner.cpp"]
 OUT = os.path.join(HERE, "libtnb200.so")
 FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
          "-std=c++17", "--cudart", "static"]

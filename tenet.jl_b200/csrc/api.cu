@@ -28,6 +28,11 @@ void pack_tables(StepSpec& S, std::vector<int64_t>& blob) {
         t->hi_pos = blob.size();
         blob.insert(blob.end(), t->hi.begin(), t->hi.end());
     }
+    if (S.st_ok) {
+        S.st_hi_pos = blob.size();  blob.insert(blob.end(), S.st_hi.begin(), S.st_hi.end());
+        S.st_rel_pos = blob.size(); blob.insert(blob.end(), S.st_rel.begin(), S.st_rel.end());
+        S.st_pos_pos = blob.size(); blob.insert(blob.end(), S.st_pos.begin(), S.st_pos.end());
+    }
 }
 
 TabRef make_ref(const HostTable& t, const int64_t* dev_blob) {
@@ -78,6 +83,10 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
             S.kernel = TNB_KERNEL_STREAM; S.splitk = thin; S.kchunk = kchunk;
             return ws_elems;
         }
+        if (S.st_ok && (dtype == TNB_C64 || dtype == TNB_C128)) {
+            S.kernel = TNB_KERNEL_STEM;
+            return 0;
+        }
         const bool tc_ok = dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT) &&
                            (double)S.M * (double)S.N * (double)S.K >= (double)(1ll << 18);
         if (tc_ok) {
@@ -119,6 +128,20 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
     a.A = A; a.B = B; a.C = C;
     a.alpha[0] = alpha[0]; a.alpha[1] = alpha[1];
     a.beta[0] = beta[0]; a.beta[1] = beta[1];
+    if (S.kernel == TNB_KERNEL_STEM) {
+        StemArgs t;
+        memset(&t, 0, sizeof t);
+        const bool sw = S.st_swap;
+        t.A = sw ? B : A; t.B = sw ? A : B; t.C = (char*)C + 0;
+        t.M = sw ? S.N : S.M; t.N = (int32_t)(sw ? S.M : S.N); t.K = (int32_t)S.K;
+        t.lda = S.K > 1 ? (sw ? S.bk.stride : S.ak.stride) : t.M;
+        t.TM = S.st_tm; t.contig = S.st_contig ? 1 : 0;
+        t.conjA = sw ? S.conjB : S.conjA; t.conjB = sw ? S.conjA : S.conjB;
+        t.bn = sw ? a.am : a.bn; t.bk = sw ? a.ak : a.bk;
+        t.hi = dev_blob + S.st_hi_pos; t.rel = dev_blob + S.st_rel_pos; t.pos = dev_blob + S.st_pos_pos;
+        t.alpha[0] = alpha[0]; t.alpha[1] = alpha[1]; t.beta[0] = beta[0]; t.beta[1] = beta[1];
+        return tnb_launch_stem(ctx, dtype, t);
+    }
     if (S.kernel == TNB_KERNEL_C64_TF32) {
         int64_t lda = S.K > 1 ? S.ak.stride : S.M, ldb = S.K > 1 ? S.bk.stride : S.N;
         if (S.tc_swap) {   // C^T = B * A^T : swap operand roles, the offset tables of C swap with them

@@ -1,0 +1,163 @@
+// kernels_stem.cu — the HBM-bound streaming kernel for "stem" steps of a sliced contraction tree:
+//
+//   C[m, n] = alpha * sum_k A[m, k] * B[n, k] (+ beta * C)      M huge (>= 2^16), N <= 16, K <= 64
+//
+// i.e. a huge dense intermediate absorbing a tiny tensor (a gate, a small environment) — the shape that dominates the
+// BYTES of a good contraction path (profiles/r1_steps_sycamore_opt.md: arithmetic intensity 2-16 flop/B, far below
+// the ridge).  What it replaces: Muscle.binary_einsum's permutedims + gemm for these calls
+// (/root/reference/src/Operations/overlap.jl:12 -> contract -> binary_einsum), where the permute
+// passes alone triple the traffic.  Here each operand element is read once and each result element written once:
+//
+//   * A is dense [K][M] (m fastest, the planner's layout): a thread owns VM consecutive m and issues one 16-byte load
+//     per k — K independent loads in flight per thread, fully coalesced across the warp;
+//   * B (<= 1024 elements) is gathered once per CTA into shared memory and read by broadcast;
+//   * the N results of each m go to a shared-memory tile at the RANK their address has inside the tile's output
+//     pattern (pos table); the tile is then written to C in ascending address order (rel table, or plain
+//     contiguous when the planner found the pattern to be one block) — consecutive lanes write consecutive
+//     addresses whatever the consumer's layout is.
+// Persistent grid (a few CTAs per SM, tiles strided over CTAs).  Algorithmic bytes per launch: sizeof(T)*(M*K + M*N).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tnb_internal.h"
+
+namespace {
+
+constexpr int ST_THREADS = 256;
+
+__device__ __forceinline__ int64_t stab(const TabRef& t, uint32_t i) {
+    uint32_t q = i / t.lo_size;
+    uint32_t r = i - q * t.lo_size;
+    return t.hi[q] + t.lo[r];
+}
+
+__device__ __forceinline__ void cmac(float2& c, float2 a, float2 b) {
+    c.x = fmaf(a.x, b.x, c.x); c.x = fmaf(-a.y, b.y, c.x);
+    c.y = fmaf(a.x, b.y, c.y); c.y = fmaf(a.y, b.x, c.y);
+}
+__device__ __forceinline__ void cmac(double2& c, double2 a, double2 b) {
+    c.x = fma(a.x, b.x, c.x); c.x = fma(-a.y, b.y, c.x);
+    c.y = fma(a.x, b.y, c.y); c.y = fma(a.y, b.x, c.y);
+}
+__device__ __forceinline__ float2 cscale(const double* s, float2 a) {
+    float sr = (float)s[0], si = (float)s[1];
+    return make_float2(sr * a.x - si * a.y, sr * a.y + si * a.x);
+}
+__device__ __forceinline__ double2 cscale(const double* s, double2 a) {
+    return make_double2(s[0] * a.x - s[1] * a.y, s[0] * a.y + s[1] * a.x);
+}
+__device__ __forceinline__ float2 czero(float2*) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ double2 czero(double2*) { return make_double2(0., 0.); }
+
+// E = float2 (VM = 2: one 16-byte load covers two m) or double2 (VM = 1)
+template <typename E, int VM, int NMAX>
+__global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int N = p.N, K = p.K, TM = p.TM;
+    E* Bs = reinterpret_cast<E*>(st_smem);                                   // [K][N]
+    E* tile = Bs + ((K * N + 1) & ~1);                                       // [TM*N] in output-rank order
+    uint16_t* pos16 = reinterpret_cast<uint16_t*>(tile + TM * N);            // [TM*N]
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < K * N; i += ST_THREADS) {
+        const int n = i % N, k = i / N;
+        E v = reinterpret_cast<const E*>(p.B)[stab(p.bn, n) + stab(p.bk, k)];
+        if (p.conjB) v.y = -v.y;
+        Bs[k * N + n] = v;
+    }
+    for (int i = tid; i < TM * N; i += ST_THREADS) pos16[i] = (uint16_t)p.pos[i];
+    __syncthreads();
+
+    const E* __restrict__ A = reinterpret_cast<const E*>(p.A);
+    E* __restrict__ C = reinterpret_cast<E*>(p.C);
+    const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
+    const bool unit_alpha = p.alpha[0] == 1.0 && p.alpha[1] == 0.0;
+    const int64_t ntiles = p.M / TM;
+    const int cnt = TM * N;
+    struct __align__(16) Vec { E v[VM]; };
+
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t m0 = t * TM;
+        for (int ml = tid * VM; ml < TM; ml += ST_THREADS * VM) {
+            E acc[VM][NMAX];
+#pragma unroll
+            for (int v = 0; v < VM; v++)
+#pragma unroll
+                for (int n = 0; n < NMAX; n++) acc[v][n] = czero((E*)0);
+            const E* src = A + m0 + ml;
+#pragma unroll 4
+            for (int k = 0; k < K; k++) {
+                Vec a = *reinterpret_cast<const Vec*>(src + (int64_t)k * p.lda);
+                if (p.conjA) {
+#pragma unroll
+                    for (int v = 0; v < VM; v++) a.v[v].y = -a.v[v].y;
+                }
+                const E* brow = Bs + k * N;
+#pragma unroll
+                for (int n = 0; n < NMAX; n++) {
+                    if (n < N) {
+                        const E b = brow[n];
+#pragma unroll
+                        for (int v = 0; v < VM; v++) cmac(acc[v][n], a.v[v], b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VM; v++)
+#pragma unroll
+                for (int n = 0; n < NMAX; n++)
+                    if (n < N) tile[pos16[(ml + v) * N + n]] = acc[v][n];
+        }
+        __syncthreads();
+        E* base = C + p.hi[t];
+        for (int j = tid; j < cnt; j += ST_THREADS) {
+            E* dst = base + (p.contig ? (p.rel[0] + j) : p.rel[j]);
+            E v = tile[j];
+            if (!unit_alpha) v = cscale(p.alpha, v);
+            if (has_beta) {
+                E o = cscale(p.beta, *dst);
+                v.x += o.x; v.y += o.y;
+            }
+            *dst = v;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename E, int VM>
+int launch(tnb_ctx* ctx, const StemArgs& a) {
+    const size_t esz = sizeof(E);
+    const size_t smem = (((size_t)a.K * a.N + 1) & ~(size_t)1) * esz + (size_t)a.TM * a.N * esz + (size_t)a.TM * a.N * 2;
+    const int64_t ntiles = a.M / a.TM;
+    int64_t per_sm = smem > 0 ? (int64_t)(200 * 1024 / smem) : 8;
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)ctx->sm_count * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return TNB_OK;
+#define ST_LAUNCH(NMAX)                                                                                            \
+    do {                                                                                                           \
+        if (smem > 48 * 1024)                                                                                      \
+            TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(stem_kernel<E, VM, NMAX>,                                     \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        stem_kernel<E, VM, NMAX><<<(unsigned)grid, ST_THREADS, smem, ctx->stream>>>(a);                            \
+    } while (0)
+    if (a.N <= 4) ST_LAUNCH(4);
+    else if (a.N <= 8) ST_LAUNCH(8);
+    else ST_LAUNCH(16);
+#undef ST_LAUNCH
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+}  // namespace
+
+int tnb_launch_stem(tnb_ctx* ctx, int dtype, const StemArgs& a) {
+    if (dtype == TNB_C64) {
+        // 16-byte loads need an even leading dimension and a 16-byte aligned base; otherwise one m per thread
+        if ((a.lda % 2) == 0 && ((uintptr_t)a.A % 16) == 0) return launch<float2, 2>(ctx, a);
+        return launch<float2, 1>(ctx, a);
+    }
+    if (dtype == TNB_C128) return launch<double2, 1>(ctx, a);
+    return tnb_set_error(ctx, TNB_EUNSUPPORTED, "stem kernel: unsupported dtype %d", dtype);
+}

@@ -31,14 +31,15 @@ std::string fmt_mode(const char* what, int32_t mode) {
 
 // Build the two-level table of one index group for one tensor.
 // modes are ordered fastest-first; strides[i] is the tensor's stride for modes[i] (0 if absent).
-void build_table(const std::vector<int64_t>& ext, const std::vector<int64_t>& strides, HostTable* t) {
+void build_table(const std::vector<int64_t>& ext, const std::vector<int64_t>& strides, HostTable* t,
+                 int64_t lo_max = 4096) {
     const size_t n = ext.size();
     t->size = 1;
     for (size_t i = 0; i < n; i++) t->size *= ext[i];
     // lo prefix
     size_t npre = 0;
     int64_t lo = 1;
-    const int64_t LO_MAX = 4096;
+    const int64_t LO_MAX = lo_max;
     while (npre < n && (npre == 0 || lo * ext[npre] <= LO_MAX)) {
         lo *= ext[npre];
         npre++;
@@ -211,6 +212,43 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
                  (S.K == 1 || S.ak.stride == S.M);
     S.b_nmajor = S.L == 1 && S.bn.affine && (S.N == 1 || S.bn.stride == 1) && S.bk.affine &&
                  (S.K == 1 || S.bk.stride == S.N);
+    // "stem" steps: a huge dense operand times a tiny one (N <= 16, K <= 64) — HBM-bound.  The streaming kernel
+    // walks the big free group in tiles of TM = lo_size of a re-grouped output table, so that every tile's
+    // output addresses are  hi[tile] + (tile-invariant pattern);  the pattern is sorted once here (rel) together
+    // with its inverse (pos), which lets the kernel write each tile in ascending address order (coalesced).
+    S.st_ok = false;
+    for (int sw = 0; sw < 2 && !S.st_ok; sw++) {
+        const std::vector<Ent>& big = sw ? gn : gm;
+        const std::vector<Ent>& small = sw ? gm : gn;
+        const int64_t Mb = sw ? S.N : S.M, Ns = sw ? S.M : S.N;
+        const bool dense = sw ? S.b_nmajor : S.a_mmajor;
+        if (S.L != 1 || !dense || Ns > 16 || S.K > 64 || Mb < 65536) continue;
+        std::vector<int64_t> ext, st;
+        for (auto& e : big) { ext.push_back(e.ext); st.push_back(e.sc); }
+        HostTable cb;
+        build_table(ext, st, &cb, std::max<int64_t>(64, 4096 / std::max<int64_t>(Ns, 1)));
+        const int64_t TM = cb.lo_size;
+        if (TM < 64 || TM > 4096 || TM * Ns > 8192 || (TM % 2)) continue;
+        std::vector<int64_t> ext2, st2;
+        for (auto& e : small) { ext2.push_back(e.ext); st2.push_back(e.sc); }
+        HostTable cs;
+        build_table(ext2, st2, &cs);
+        const int64_t cnt = TM * Ns;
+        std::vector<std::pair<int64_t, int64_t>> addr((size_t)cnt);
+        for (int64_t ml = 0; ml < TM; ml++)
+            for (int64_t n = 0; n < Ns; n++) addr[(size_t)(ml * Ns + n)] = {cb.lo[(size_t)ml] + cs.at(n), ml * Ns + n};
+        std::sort(addr.begin(), addr.end());
+        S.st_rel.assign((size_t)cnt, 0);
+        S.st_pos.assign((size_t)cnt, 0);
+        bool contig = true;
+        for (int64_t j = 0; j < cnt; j++) {
+            S.st_rel[(size_t)j] = addr[(size_t)j].first;
+            S.st_pos[(size_t)addr[(size_t)j].second] = j;
+            if (addr[(size_t)j].first != addr[0].first + j) contig = false;
+        }
+        S.st_hi = cb.hi;
+        S.st_ok = true; S.st_swap = sw != 0; S.st_tm = (int32_t)TM; S.st_contig = contig;
+    }
     double macs = (double)S.M * (double)S.N * (double)S.K * (double)S.L;
     S.flops = (cplx ? 8.0 : 2.0) * macs;
     auto elems = [](const PlanTensor& T) {

@@ -71,6 +71,11 @@ struct StepSpec {
     // fast-kernel eligibility facts (filled by the planner)
     bool a_mmajor = false;   // A[m + M*k] exactly (dense, M fastest), no conj needed handled separately
     bool b_nmajor = false;
+    // streaming "stem" kernel (huge dense operand x tiny operand): tile-invariant sorted output pattern
+    bool st_ok = false, st_swap = false, st_contig = false;
+    int32_t st_tm = 0;
+    std::vector<int64_t> st_hi, st_rel, st_pos;
+    size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
     int32_t tc_nt = 0;       // tcgen05 kernel: N tile (256/128), 0 = not used
     bool tc_swap = false;    // tcgen05 kernel: operands swapped (C^T = B A^T)
 };
@@ -136,6 +141,21 @@ int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);
 int tnb_tc_c64_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t* kb_per_split, int64_t* ws_elems);
+
+// kernels_stem.cu
+struct StemArgs {
+    const void* A;            // big operand, dense [K][M] (m fastest)
+    const void* B;            // tiny operand, gathered through bn/bk
+    void* C;
+    int64_t M, lda;
+    int32_t N, K, TM, contig, conjA, conjB;
+    TabRef bn, bk;
+    const int64_t* hi;        // [M/TM] tile base offsets in C
+    const int64_t* rel;       // [TM*N] ascending offsets inside a tile
+    const int64_t* pos;       // [TM*N] (ml*N+n) -> rank in rel
+    double alpha[2], beta[2];
+};
+int tnb_launch_stem(tnb_ctx* ctx, int dtype, const StemArgs& a);
 
 // kernels_c128_dmma.cu
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);

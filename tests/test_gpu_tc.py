@@ -127,3 +127,42 @@ def test_tc_misaligned_view_falls_back(ctx):
     c = tb.binary_einsum(v, tb.Tensor(b, ("n", "k")))
     ref = big[1:129].astype(np.complex128) @ b.astype(np.complex128).T
     assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("dt,tol", [(np.complex64, 2e-6), (np.complex128, 1e-13)])
+def test_stem_stream_kernel(ctx, dt, tol):
+    """HBM-bound stem steps: huge dense operand x tiny operand, consumer layouts that interleave the tiny
+    operand's modes with the big one's (sorted tile pattern), both orientations, conj flags."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(31)
+    big_modes = [f"m{i}" for i in range(17)]
+    a = crand(rng, (2,) * 17 + (2, 2), dt)                       # m0..m16 | k0 k1   -> M = 2^17, K = 4
+    b = crand(rng, (2, 2, 2, 2, 2), dt)                          # n0 n1 n2 | k0 k1  -> N = 8
+    ta = tb.Tensor(a, big_modes + ["k0", "k1"])
+    tb_ = tb.Tensor(b, ["n0", "n1", "n2", "k0", "k1"])
+    hi = np.complex128
+    ref = np.einsum(a.astype(hi), list(range(19)), b.astype(hi), [19, 20, 21, 17, 18], list(range(17)) + [19, 20, 21])
+    ref_inds = big_modes + ["n0", "n1", "n2"]
+    outs = [None,
+            ["n0"] + big_modes[:3] + ["n1"] + big_modes[3:9] + ["n2"] + big_modes[9:],       # tiny modes interleaved
+            big_modes[5:] + ["n2", "n1", "n0"] + big_modes[:5]]                               # big modes reordered too
+    for out in outs:
+        c = tb.binary_einsum(ta, tb_, out=out)
+        assert ctx.last_kernel == "stem", ctx.last_kernel
+        r = ref if out is None else np.transpose(ref, [ref_inds.index(i) for i in out])
+        assert np.abs(c.parent - r).max() / np.abs(r).max() < tol
+    # swapped orientation + conj on both
+    c = tb.binary_einsum(tb_.conj(), ta.conj())
+    assert ctx.last_kernel == "stem"
+    r = np.conj(np.transpose(ref, [17, 18, 19] + list(range(17))))
+    assert np.abs(c.parent - r).max() / np.abs(r).max() < tol
+    # K = 1 (outer product with a tiny tensor) and N = 16, K = 16
+    a2 = crand(rng, (1 << 16,), dt)
+    b2 = crand(rng, (4,), dt)
+    c = tb.binary_einsum(tb.Tensor(a2, ["m"]), tb.Tensor(b2, ["n"]))
+    assert np.abs(c.parent - np.outer(a2.astype(hi), b2.astype(hi))).max() < tol * 10
+    a3, b3 = crand(rng, (1 << 16, 16), dt), crand(rng, (16, 16), dt)
+    c = tb.binary_einsum(tb.Tensor(a3, ["m", "k"]), tb.Tensor(b3, ["n", "k"]), out=["n", "m"])
+    assert ctx.last_kernel == "stem"
+    r = (a3.astype(hi) @ b3.astype(hi).T).T
+    assert np.abs(c.parent - r).max() / np.abs(r).max() < tol * 4
