@@ -162,6 +162,7 @@ typedef struct tnb_step_info {
 #define TNB_KERNEL_STREAM    3    /* memory-bound streaming kernel (small K*N)               */
 #define TNB_KERNEL_SPLITK    4    /* split-K reduction (M*N tiny, K huge)                    */
 #define TNB_KERNEL_STEM      5    /* HBM-bound streaming kernel: huge dense operand x tiny operand */
+#define TNB_KERNEL_STEM_TC   6    /* persistent tcgen05 kernel: huge dense operand x small operand (16 <= N <= 64) */
 int tnb_plan_get_step(const tnb_plan* plan, int32_t step, tnb_step_info* info);
 
 /* per-step device timing (CUDA events on the context stream; one host sync per slice while enabled) */

@@ -18,7 +18,7 @@ TNB_OK, TNB_EINVAL, TNB_ENOMEM, TNB_ECUDA, TNB_ENCCL, TNB_EUNSUPPORTED = range(6
 TNB_C128, TNB_C64, TNB_F64, TNB_F32 = range(4)
 TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL = 1, 2
 TNB_C64_SIMT, TNB_C64_TF32X3, TNB_C64_TF32X3_FAST = 0, 1, 2
-KERNEL_NAMES = {0: "generic", 1: "c64_tf32x3", 2: "c128_dmma", 3: "stream", 4: "splitk", 5: "stem"}
+KERNEL_NAMES = {0: "generic", 1: "c64_tf32x3", 2: "c128_dmma", 3: "stream", 4: "splitk", 5: "stem", 6: "stem_tc"}
 
 DTYPE_CODE = {np.dtype(np.complex128): TNB_C128, np.dtype(np.complex64): TNB_C64,
               np.dtype(np.float64): TNB_F64, np.dtype(np.float32): TNB_F32}

@@ -83,8 +83,12 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
             S.kernel = TNB_KERNEL_STREAM; S.splitk = thin; S.kchunk = kchunk;
             return ws_elems;
         }
-        if (S.st_ok && (dtype == TNB_C64 || dtype == TNB_C128)) {
+        if (S.st_ok && !S.st_tc && (dtype == TNB_C64 || dtype == TNB_C128)) {
             S.kernel = TNB_KERNEL_STEM;
+            return 0;
+        }
+        if (S.st_ok && S.st_tc && dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT)) {
+            S.kernel = TNB_KERNEL_STEM_TC;
             return 0;
         }
         const bool tc_ok = dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT) &&
@@ -128,7 +132,7 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
     a.A = A; a.B = B; a.C = C;
     a.alpha[0] = alpha[0]; a.alpha[1] = alpha[1];
     a.beta[0] = beta[0]; a.beta[1] = beta[1];
-    if (S.kernel == TNB_KERNEL_STEM) {
+    if (S.kernel == TNB_KERNEL_STEM || S.kernel == TNB_KERNEL_STEM_TC) {
         StemArgs t;
         memset(&t, 0, sizeof t);
         const bool sw = S.st_swap;
@@ -140,7 +144,10 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         t.bn = sw ? a.am : a.bn; t.bk = sw ? a.ak : a.bk;
         t.hi = dev_blob + S.st_hi_pos; t.rel = dev_blob + S.st_rel_pos; t.pos = dev_blob + S.st_pos_pos;
         t.alpha[0] = alpha[0]; t.alpha[1] = alpha[1]; t.beta[0] = beta[0]; t.beta[1] = beta[1];
-        return tnb_launch_stem(ctx, dtype, t);
+        if (S.kernel == TNB_KERNEL_STEM) return tnb_launch_stem(ctx, dtype, t);
+        int rc = tnb_launch_c64_stem_tc(ctx, t);
+        if (rc != -1) return rc;
+        return tnb_launch_einsum_generic(ctx, dtype, a);          // misaligned big operand: exact-FP32 generic kernel
     }
     if (S.kernel == TNB_KERNEL_C64_TF32) {
         int64_t lda = S.K > 1 ? S.ak.stride : S.M, ldb = S.K > 1 ? S.bk.stride : S.N;

@@ -645,6 +645,247 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
     return TNB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 64, K <= 128.
+//
+// These steps carry most of the BYTES of a good sliced path (arithmetic intensity 13-43 flop/B, below the ridge), so
+// the kernel is organised around HBM, not around the tensor pipe:
+//   * one persistent CTA per SM walks 128-row tiles of the big operand; its A tile rows arrive by cp.async.bulk
+//     (8 KB per 8 k) into a raw ring, every A byte is read from HBM exactly once;
+//   * the small operand is gathered, split (hi/lo, re/im) and laid out as UMMA planes ONCE per CTA for all of K
+//     (<= 64 KB) and stays resident;
+//   * 8 worker warps split the raw A tiles into planes, one thread issues 12 x kind::tf32 MMAs (N wide) per 8 k into
+//     one of two TMEM accumulator sets;
+//   * 4 epilogue warps drain the other set (tcgen05.ld), drop each value at the RANK of its output address inside
+//     the tile's (tile-invariant, planner-sorted) address pattern in a shared staging tile, and write the tile to C
+//     in ascending address order — coalesced whatever layout the consumer asked for.  Drain of tile i overlaps the
+//     copies, splits and MMAs of tile i+1.
+// Chain length in TMEM is 6*K/8 <= 96 MMAs (K <= 128): the round-toward-zero bias stays ~6e-6 relative.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SK_WORKERS = 256;                 // warps 0-7
+constexpr int SK_THREADS = SK_WORKERS + 128 + 64;   // + epilogue warps 8-11, MMA warp 12, copy warp 13
+constexpr int SK_RAW = 3, SK_PL = 3;
+
+struct StemTcArgs {
+    const float2* A;          // dense [K][M]
+    const float2* B;          // small operand, gathered through bn/bk
+    float2* C;
+    int64_t M, lda;
+    int32_t N, K, contig, conjA, conjB;
+    TabRef bn, bk;
+    const int64_t* hi;        // [M/128]
+    const int64_t* rel;       // [128*N]
+    const int64_t* pos;       // [128*N]
+    float alpha[2], beta[2];
+};
+
+struct SkSmem {
+    // B planes: 4 * (K/8) * N * 32 B <= 64 KB; A raw ring; A planes ring; staging tile 128*N*8 <= 64 KB
+    static constexpr int BPL_MAX = 64 * 1024;
+    static constexpr int RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
+    static constexpr int APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
+    static constexpr int RAW_OFF = BPL_MAX;
+    static constexpr int APL_OFF = RAW_OFF + SK_RAW * RAW_STAGE;
+    static constexpr int STG_OFF = APL_OFF + SK_PL * APL_STAGE;
+    static constexpr int STG_MAX = 64 * 1024;
+    static constexpr int BAR_OFF = STG_OFF + STG_MAX;              // raw_full/empty[R], apl_full/empty[P], accfull/empty[2]
+    static constexpr int NBARS = 2 * SK_RAW + 2 * SK_PL + 4;
+    static constexpr int TMEM_OFF = BAR_OFF + NBARS * 8;
+    static constexpr int TOTAL = TMEM_OFF + 16;
+};
+
+template <int NT>   // UMMA N (16, 32, 64)
+__global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p) {
+    using S = SkSmem;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nkb = (uint32_t)p.K / TC_BK;
+    const int64_t ntiles = p.M / TC_BM;
+    constexpr int B_PLANE_KB = NT * TC_BK * 4;                       // bytes of one B plane for one k-block
+    const uint32_t b_plane = nkb * B_PLANE_KB;                       // bytes of one B plane (all k)
+
+    const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
+    auto raw_full = [&](int s) { return bar0 + 8u * s; };
+    auto raw_empty = [&](int s) { return bar0 + 8u * (SK_RAW + s); };
+    auto apl_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW + s); };
+    auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW + SK_PL + s); };
+    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW + 2 * SK_PL + s); };
+    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW + 2 * SK_PL + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
+    constexpr uint32_t TMEM_COLS = (4 * NT) < 32 ? 32 : 4 * NT;      // two sets of [re NT | im NT]
+
+    if (tid == 0) {
+        for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 32); }
+        for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 32); mbar_init(apl_empty(s), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    // small operand -> resident planes (all k-blocks): plane q at q*b_plane, k-block kb at kb*B_PLANE_KB
+    for (uint32_t u = tid; u < (uint32_t)NT * nkb * 2; u += SK_THREADS) {
+        const uint32_t row = u % NT, r = u / NT, kc = r & 1, kb = r >> 1;
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t k = kb * TC_BK + kc * 4 + i;
+            v[i] = (int)row < p.N ? p.B[tabc(p.bn, row) + tabc(p.bk, k)] : make_float2(0.f, 0.f);
+        }
+        split_store(smem + kb * B_PLANE_KB, (int)b_plane, (int)row, (int)kc, v, p.conjB);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ---- workers: raw A tile -> planes ----
+        const int prow = tid & 127, pkc = tid >> 7;
+        const int raw_base = S::RAW_OFF + (pkc * 4 * TC_BM + prow) * 8;
+        int rs = 0, ps = 0;
+        uint32_t rphase = 0, pphase = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t kb = 0; kb < nkb; kb++) {
+                mbar_wait(raw_full(rs), rphase);
+                float2 v[4];
+                const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                mbar_wait(apl_empty(ps), pphase ^ 1);
+                split_store(smem + S::APL_OFF + ps * S::APL_STAGE, TC_BM * TC_BK * 4, prow, pkc, v, p.conjA);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
+                if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
+                if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
+            }
+        }
+    } else if (warp < 12) {
+        // ---- epilogue warps: TMEM -> staging (rank order) -> C (ascending addresses) ----
+        const int q = warp & 3;
+        const int etid = tid - SK_WORKERS;                         // 0..127
+        const uint32_t row = q * 32 + lane;
+        float2* stg = reinterpret_cast<float2*>(smem + S::STG_OFF);
+        const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
+        const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+        const int cnt = TC_BM * p.N;
+        uint32_t i = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+            const uint32_t set = i & 1;
+            mbar_wait(accfull_bar(set), (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
+            const int64_t* prow = p.pos + (int64_t)row * p.N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+                uint32_t re[16], im[16];
+                tmem_ld16(taddr + c0, re);
+                tmem_ld16(taddr + NT + c0, im);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (c0 + j < p.N) stg[prow[c0 + j]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: next-next tile may start
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // staging tile complete (epilogue warps only)
+            float2* base = p.C + p.hi[t];
+            for (int j = etid; j < cnt; j += 128) {
+                float2 v = stg[j];
+                float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
+                float2* dst = base + (p.contig ? (p.rel[0] + j) : p.rel[j]);
+                if (has_beta) {
+                    float2 old = *dst;
+                    o.x += br * old.x - bi * old.y;
+                    o.y += br * old.y + bi * old.x;
+                }
+                *dst = o;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // staging tile free again
+        }
+    } else if (warp == 12) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
+            int ps = 0;
+            uint32_t pphase = 0, i = 0;
+            const uint32_t sb0 = smem_u32(smem);
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+                const uint32_t set = i & 1;
+                if (i >= 2) { mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1); tc_fence_after(); }
+                const uint32_t d_re = tmem_base + set * (2u * NT), d_im = d_re + NT;
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    mbar_wait(apl_full(ps), pphase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + S::APL_OFF + ps * S::APL_STAGE);
+                    constexpr uint32_t AP = TC_BM * TC_BK * 4;
+                    const uint32_t sb = sb0 + kb * B_PLANE_KB;
+                    const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + AP),
+                                   a_ih = make_smem_desc(sa + 2 * AP), a_il = make_smem_desc(sa + 3 * AP);
+                    const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + b_plane),
+                                   b_ih = make_smem_desc(sb + 2 * b_plane), b_il = make_smem_desc(sb + 3 * b_plane);
+                    const uint32_t acc = kb > 0 ? 1u : 0u;
+                    umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
+                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_im, a_rh, b_il, IDESC, acc);
+                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                    umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_commit(apl_empty(ps));
+                    if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
+                }
+                umma_commit(accfull_bar(set));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile ----
+        int rs = 0;
+        uint32_t rphase = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const float2* src = p.A + t * TC_BM;
+            for (uint32_t kb = 0; kb < nkb; kb++) {
+                mbar_wait(raw_empty(rs), rphase ^ 1);
+                if (lane == 0) mbar_expect_tx(raw_full(rs), S::RAW_STAGE);
+                __syncwarp();
+                if (lane < 8) {
+                    const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + lane * TC_BM * 8);
+                    bulk_g2s(dst, src + (int64_t)(kb * TC_BK + lane) * p.lda, TC_BM * 8, raw_full(rs));
+                }
+                if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int NT>
+int launch_stem_tc(tnb_ctx* ctx, const StemTcArgs& a) {
+    static bool configured[16] = {false};
+    if (!configured[ctx->device & 15]) {
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::TOTAL));
+        configured[ctx->device & 15] = true;
+    }
+    int64_t grid = a.M / TC_BM;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    c64_tf32x3_stem_kernel<NT><<<(unsigned)grid, SK_THREADS, SkSmem::TOTAL, ctx->stream>>>(a);
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
 // cp.async.bulk needs 16-byte aligned rows: even M, N and leading dimensions, 16-byte aligned bases
 bool tc_acc_ok(const TcArgs& a) {
     return (a.M % 2) == 0 && (a.N % 2) == 0 && (a.lda % 2) == 0 && (a.ldb % 2) == 0 &&
@@ -705,4 +946,24 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
     }
     if (!tc_acc_ok(a)) return -1;
     return launch_tc_acc(ctx, a);
+}
+
+// Plan-time eligibility of the persistent tensor-core stem kernel (sizes only; density is checked by the planner).
+bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
+    return Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K <= 128 &&
+           K % TC_BK == 0 && Nsmall * K * 16 <= SkSmem::BPL_MAX;
+}
+
+// returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back)
+int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
+    if ((e.lda % 2) != 0 || ((uintptr_t)e.A % 16) != 0) return -1;
+    StemTcArgs a;
+    a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
+    a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.contig = e.contig; a.conjA = e.conjA; a.conjB = e.conjB;
+    a.bn = e.bn; a.bk = e.bk; a.hi = e.hi; a.rel = e.rel; a.pos = e.pos;
+    a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
+    a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
+    if (e.N <= 16) return launch_stem_tc<16>(ctx, a);
+    if (e.N <= 32) return launch_stem_tc<32>(ctx, a);
+    return launch_stem_tc<64>(ctx, a);
 }

@@ -58,13 +58,13 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
     uint16_t* pos16 = reinterpret_cast<uint16_t*>(tile + TM * N);            // [TM*N]
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < K * N; i += ST_THREADS) {
+    for (int i = tid; i < K * N; i += (int)blockDim.x) {
         const int n = i % N, k = i / N;
         E v = reinterpret_cast<const E*>(p.B)[stab(p.bn, n) + stab(p.bk, k)];
         if (p.conjB) v.y = -v.y;
         Bs[k * N + n] = v;
     }
-    for (int i = tid; i < TM * N; i += ST_THREADS) pos16[i] = (uint16_t)p.pos[i];
+    for (int i = tid; i < TM * N; i += (int)blockDim.x) pos16[i] = (uint16_t)p.pos[i];
     __syncthreads();
 
     const E* __restrict__ A = reinterpret_cast<const E*>(p.A);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t m0 = t * TM;
-        for (int ml = tid * VM; ml < TM; ml += ST_THREADS * VM) {
+        for (int ml = tid * VM; ml < TM; ml += (int)blockDim.x * VM) {
             E acc[VM][NMAX];
 #pragma unroll
             for (int v = 0; v < VM; v++)
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
         }
         __syncthreads();
         E* base = C + p.hi[t];
-        for (int j = tid; j < cnt; j += ST_THREADS) {
+        for (int j = tid; j < cnt; j += (int)blockDim.x) {
             E* dst = base + (p.contig ? (p.rel[0] + j) : p.rel[j]);
             E v = tile[j];
             if (!unit_alpha) v = cscale(p.alpha, v);
@@ -128,8 +128,14 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
     const size_t esz = sizeof(E);
     const size_t smem = (((size_t)a.K * a.N + 1) & ~(size_t)1) * esz + (size_t)a.TM * a.N * esz + (size_t)a.TM * a.N * 2;
     const int64_t ntiles = a.M / a.TM;
+    // every thread owns VM consecutive m of a tile: no idle lanes in the compute phase
+    int threads = (int)(a.TM / VM);
+    if (threads > ST_THREADS) threads = ST_THREADS;
+    threads = (threads + 31) / 32 * 32;
     int64_t per_sm = smem > 0 ? (int64_t)(200 * 1024 / smem) : 8;
-    if (per_sm > 6) per_sm = 6;
+    const int64_t by_threads = 2048 / threads;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;
@@ -139,7 +145,7 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
         if (smem > 48 * 1024)                                                                                      \
             TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(stem_kernel<E, VM, NMAX>,                                     \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        stem_kernel<E, VM, NMAX><<<(unsigned)grid, ST_THREADS, smem, ctx->stream>>>(a);                            \
+        stem_kernel<E, VM, NMAX><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);                            \
     } while (0)
     if (a.N <= 4) ST_LAUNCH(4);
     else if (a.N <= 8) ST_LAUNCH(8);

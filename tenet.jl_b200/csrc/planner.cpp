@@ -222,13 +222,30 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         const std::vector<Ent>& small = sw ? gm : gn;
         const int64_t Mb = sw ? S.N : S.M, Ns = sw ? S.M : S.N;
         const bool dense = sw ? S.b_nmajor : S.a_mmajor;
-        if (S.L != 1 || !dense || Ns > 16 || S.K > 64 || Mb < 65536) continue;
+        if (S.L != 1 || !dense || Mb < 65536) continue;
+        // class 1: SIMT streaming (N*K small: FP32 FMA keeps up with HBM); class 2: tensor-core stem (c64 only)
+        const bool tcst = cplx && elem_size == 8 && tnb_stem_tc_shape_ok(Mb, Ns, S.K);
+        const bool simt = !tcst && Ns <= 16 && S.K <= 64;
+        if (!simt && !tcst) continue;
+        const int64_t lo_max = simt ? std::max<int64_t>(64, 8192 / std::max<int64_t>(Ns, 1)) : 128;
         std::vector<int64_t> ext, st;
-        for (auto& e : big) { ext.push_back(e.ext); st.push_back(e.sc); }
+        for (auto& e : big) {
+            // a single mode longer than a tile is split (d, ext/d) with d the largest divisor that fits
+            if (ext.empty() && e.ext > lo_max) {
+                int64_t d = 1;
+                for (int64_t c = 2; c <= lo_max; c++) if (e.ext % c == 0) d = c;
+                ext.push_back(d); st.push_back(e.sc);
+                ext.push_back(e.ext / d); st.push_back(e.sc * d);
+                continue;
+            }
+            ext.push_back(e.ext); st.push_back(e.sc);
+        }
         HostTable cb;
-        build_table(ext, st, &cb, std::max<int64_t>(64, 4096 / std::max<int64_t>(Ns, 1)));
+        build_table(ext, st, &cb, lo_max);
         const int64_t TM = cb.lo_size;
         if (TM < 64 || TM > 4096 || TM * Ns > 8192 || (TM % 2)) continue;
+        if (!simt && TM != 128) continue;
+        S.st_tc = !simt;
         std::vector<int64_t> ext2, st2;
         for (auto& e : small) { ext2.push_back(e.ext); st2.push_back(e.sc); }
         HostTable cs;

@@ -72,7 +72,7 @@ struct StepSpec {
     bool a_mmajor = false;   // A[m + M*k] exactly (dense, M fastest), no conj needed handled separately
     bool b_nmajor = false;
     // streaming "stem" kernel (huge dense operand x tiny operand): tile-invariant sorted output pattern
-    bool st_ok = false, st_swap = false, st_contig = false;
+    bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
     int32_t st_tm = 0;
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
@@ -156,6 +156,8 @@ struct StemArgs {
     double alpha[2], beta[2];
 };
 int tnb_launch_stem(tnb_ctx* ctx, int dtype, const StemArgs& a);
+bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K);
+int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e);
 
 // kernels_c128_dmma.cu
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);

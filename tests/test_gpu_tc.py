@@ -161,8 +161,32 @@ def test_stem_stream_kernel(ctx, dt, tol):
     b2 = crand(rng, (4,), dt)
     c = tb.binary_einsum(tb.Tensor(a2, ["m"]), tb.Tensor(b2, ["n"]))
     assert np.abs(c.parent - np.outer(a2.astype(hi), b2.astype(hi))).max() < tol * 10
-    a3, b3 = crand(rng, (1 << 16, 16), dt), crand(rng, (16, 16), dt)
+    a3, b3 = crand(rng, (1 << 16, 16), dt), crand(rng, (8, 16), dt)
     c = tb.binary_einsum(tb.Tensor(a3, ["m", "k"]), tb.Tensor(b3, ["n", "k"]), out=["n", "m"])
     assert ctx.last_kernel == "stem"
     r = (a3.astype(hi) @ b3.astype(hi).T).T
     assert np.abs(c.parent - r).max() / np.abs(r).max() < tol * 4
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (32, 128), (64, 64), (48, 8), (64, 16)])
+def test_stem_tc_kernel(ctx, N, K):
+    """persistent tcgen05 stem kernel: huge x small, several consumer layouts, both orientations."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(N * 131 + K)
+    M = 1 << 17
+    a = crand(rng, (2,) * 17 + (K,))
+    b = crand(rng, (N, K))
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"])
+    hi = np.complex128
+    ref = np.tensordot(a.astype(hi), b.astype(hi), axes=([17], [1]))          # m0..m16, n
+    for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8]]:
+        c = tb.binary_einsum(ta, tb_, out=out)
+        assert ctx.last_kernel == "stem_tc", ctx.last_kernel
+        r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        err = np.abs(c.parent - r).max() / np.abs(r).max()
+        assert err < 1e-5, err
+    c = tb.binary_einsum(tb_.conj(), ta)
+    assert ctx.last_kernel == "stem_tc"
+    r = np.transpose(np.tensordot(a.astype(hi), np.conj(b).astype(hi), axes=([17], [1])), [17] + list(range(17)))
+    assert np.abs(c.parent - r).max() / np.abs(r).max() < 1e-5
