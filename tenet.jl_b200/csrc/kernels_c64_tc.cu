@@ -664,7 +664,9 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SK_WORKERS = 256;                 // warps 0-7
 constexpr int SK_THREADS = SK_WORKERS + 128 + 64;   // + epilogue warps 8-11, MMA warp 12, copy warp 13
-constexpr int SK_RAW = 3, SK_PL = 3;
+constexpr int SK_PL = 2;                        // A plane stages (16 KB each)
+constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as many as shared memory allows — the
+                                                // bytes in flight per SM (>= 64 KB) are what saturates HBM
 
 struct StemTcArgs {
     const float2* A;          // dense [K][M]
@@ -672,6 +674,7 @@ struct StemTcArgs {
     float2* C;
     int64_t M, lda;
     int32_t N, K, contig, conjA, conjB;
+    int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
     const int64_t* rel;       // [128*N]
@@ -679,19 +682,22 @@ struct StemTcArgs {
     float alpha[2], beta[2];
 };
 
+// shared-memory map (sizes depend on N, K): [ B planes | staging tile | A planes ring | raw ring | barriers | tmem slot ]
 struct SkSmem {
-    // B planes: 4 * (K/8) * N * 32 B <= 64 KB; A raw ring; A planes ring; staging tile 128*N*8 <= 64 KB
-    static constexpr int BPL_MAX = 64 * 1024;
     static constexpr int RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
     static constexpr int APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
-    static constexpr int RAW_OFF = BPL_MAX;
-    static constexpr int APL_OFF = RAW_OFF + SK_RAW * RAW_STAGE;
-    static constexpr int STG_OFF = APL_OFF + SK_PL * APL_STAGE;
-    static constexpr int STG_MAX = 64 * 1024;
-    static constexpr int BAR_OFF = STG_OFF + STG_MAX;              // raw_full/empty[R], apl_full/empty[P], accfull/empty[2]
-    static constexpr int NBARS = 2 * SK_RAW + 2 * SK_PL + 4;
-    static constexpr int TMEM_OFF = BAR_OFF + NBARS * 8;
-    static constexpr int TOTAL = TMEM_OFF + 16;
+    static constexpr int NBARS = 2 * SK_RAW_MAX + 2 * SK_PL + 4;
+    static constexpr int TAIL = NBARS * 8 + 16;
+    static constexpr int BUDGET = 227 * 1024;
+    __host__ __device__ static int bpl_bytes(int nt, int k) { return 4 * (k / TC_BK) * nt * TC_BK * 4; }
+    __host__ __device__ static int stg_bytes(int n) { return (TC_BM * n * 8 + 1023) / 1024 * 1024; }
+    __host__ __device__ static int apl_off(int nt, int n, int k) { return (bpl_bytes(nt, k) + 1023) / 1024 * 1024 + stg_bytes(n); }
+    __host__ __device__ static int raw_off(int nt, int n, int k) { return apl_off(nt, n, k) + SK_PL * APL_STAGE; }
+    __host__ static int raw_stages(int nt, int n, int k) {
+        int r = (BUDGET - TAIL - raw_off(nt, n, k)) / RAW_STAGE;
+        return r > SK_RAW_MAX ? SK_RAW_MAX : r;
+    }
+    __host__ __device__ static int total(int nt, int n, int k, int raw) { return raw_off(nt, n, k) + raw * RAW_STAGE + TAIL; }
 };
 
 template <int NT>   // UMMA N (16, 32, 64)
@@ -704,14 +710,18 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     constexpr int B_PLANE_KB = NT * TC_BK * 4;                       // bytes of one B plane for one k-block
     const uint32_t b_plane = nkb * B_PLANE_KB;                       // bytes of one B plane (all k)
 
-    const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
+    const int SK_RAW = p.raw_stages;
+    const int STG_OFF = (S::bpl_bytes(NT, p.K) + 1023) / 1024 * 1024;
+    const int APL_OFF = S::apl_off(NT, p.N, p.K), RAW_OFF = S::raw_off(NT, p.N, p.K);
+    const int BAR_OFF = RAW_OFF + SK_RAW * S::RAW_STAGE;
+    const uint32_t bar0 = smem_u32(smem + BAR_OFF);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
-    auto raw_empty = [&](int s) { return bar0 + 8u * (SK_RAW + s); };
-    auto apl_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW + s); };
-    auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW + SK_PL + s); };
-    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW + 2 * SK_PL + s); };
-    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW + 2 * SK_PL + 2 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
+    auto raw_empty = [&](int s) { return bar0 + 8u * (SK_RAW_MAX + s); };
+    auto apl_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + s); };
+    auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + SK_PL + s); };
+    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL + s); };
+    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + S::NBARS * 8);
     constexpr uint32_t TMEM_COLS = (4 * NT) < 32 ? 32 : 4 * NT;      // two sets of [re NT | im NT]
 
     if (tid == 0) {
@@ -741,7 +751,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     if (warp < 8) {
         // ---- workers: raw A tile -> planes ----
         const int prow = tid & 127, pkc = tid >> 7;
-        const int raw_base = S::RAW_OFF + (pkc * 4 * TC_BM + prow) * 8;
+        const int raw_base = RAW_OFF + (pkc * 4 * TC_BM + prow) * 8;
         int rs = 0, ps = 0;
         uint32_t rphase = 0, pphase = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -752,7 +762,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 #pragma unroll
                 for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
                 mbar_wait(apl_empty(ps), pphase ^ 1);
-                split_store(smem + S::APL_OFF + ps * S::APL_STAGE, TC_BM * TC_BK * 4, prow, pkc, v, p.conjA);
+                split_store(smem + APL_OFF + ps * S::APL_STAGE, TC_BM * TC_BK * 4, prow, pkc, v, p.conjA);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         const int q = warp & 3;
         const int etid = tid - SK_WORKERS;                         // 0..127
         const uint32_t row = q * 32 + lane;
-        float2* stg = reinterpret_cast<float2*>(smem + S::STG_OFF);
+        float2* stg = reinterpret_cast<float2*>(smem + STG_OFF);
         const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
         const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
         const int cnt = TC_BM * p.N;
@@ -818,7 +828,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 for (uint32_t kb = 0; kb < nkb; kb++) {
                     mbar_wait(apl_full(ps), pphase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + S::APL_OFF + ps * S::APL_STAGE);
+                    const uint32_t sa = smem_u32(smem + APL_OFF + ps * S::APL_STAGE);
                     constexpr uint32_t AP = TC_BM * TC_BK * 4;
                     const uint32_t sb = sb0 + kb * B_PLANE_KB;
                     const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + AP),
@@ -856,7 +866,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 if (lane == 0) mbar_expect_tx(raw_full(rs), S::RAW_STAGE);
                 __syncwarp();
                 if (lane < 8) {
-                    const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + lane * TC_BM * 8);
+                    const uint32_t dst = smem_u32(smem + RAW_OFF + rs * S::RAW_STAGE + lane * TC_BM * 8);
                     bulk_g2s(dst, src + (int64_t)(kb * TC_BK + lane) * p.lda, TC_BM * 8, raw_full(rs));
                 }
                 if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
@@ -872,15 +882,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 }
 
 template <int NT>
-int launch_stem_tc(tnb_ctx* ctx, const StemTcArgs& a) {
-    static bool configured[16] = {false};
-    if (!configured[ctx->device & 15]) {
-        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::TOTAL));
-        configured[ctx->device & 15] = true;
-    }
+int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
+    a.raw_stages = SkSmem::raw_stages(NT, a.N, a.K);
+    if (a.raw_stages < 3) return -1;
+    const int smem = SkSmem::total(NT, a.N, a.K, a.raw_stages);
+    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    c64_tf32x3_stem_kernel<NT><<<(unsigned)grid, SK_THREADS, SkSmem::TOTAL, ctx->stream>>>(a);
+    c64_tf32x3_stem_kernel<NT><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
@@ -951,7 +960,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
 // Plan-time eligibility of the persistent tensor-core stem kernel (sizes only; density is checked by the planner).
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
     return Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K <= 128 &&
-           K % TC_BK == 0 && Nsmall * K * 16 <= SkSmem::BPL_MAX;
+           K % TC_BK == 0 && Nsmall * K * 16 <= 64 * 1024;
 }
 
 // returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back)

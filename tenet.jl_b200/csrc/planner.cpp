@@ -227,7 +227,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         const bool tcst = cplx && elem_size == 8 && tnb_stem_tc_shape_ok(Mb, Ns, S.K);
         const bool simt = !tcst && Ns <= 16 && S.K <= 64;
         if (!simt && !tcst) continue;
-        const int64_t lo_max = simt ? std::max<int64_t>(64, 8192 / std::max<int64_t>(Ns, 1)) : 128;
+        const int64_t lo_max = simt ? std::max<int64_t>(64, 4096 / std::max<int64_t>(Ns, 1)) : 128;
         std::vector<int64_t> ext, st;
         for (auto& e : big) {
             // a single mode longer than a tile is split (d, ext/d) with d the largest divisor that fits
