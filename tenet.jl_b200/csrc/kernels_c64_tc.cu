@@ -675,6 +675,7 @@ struct StemTcArgs {
     int64_t M, lda;
     int32_t N, K, contig, conjA, conjB;
     int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
+    int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
     const int64_t* rel;       // [128*N]
@@ -691,7 +692,11 @@ struct SkSmem {
     static constexpr int BUDGET = 227 * 1024;
     __host__ __device__ static int bpl_bytes(int nt, int k) { return 4 * (k / TC_BK) * nt * TC_BK * 4; }
     __host__ __device__ static int stg_bytes(int n) { return (TC_BM * n * 8 + 1023) / 1024 * 1024; }
-    __host__ __device__ static int apl_off(int nt, int n, int k) { return (bpl_bytes(nt, k) + 1023) / 1024 * 1024 + stg_bytes(n); }
+    // after the staging tile: pos16[128*N] (rank of every (row, col), bank-swizzled) and up to 2048 run bases (int64)
+    __host__ __device__ static int tab_bytes(int n) { return (TC_BM * n * 2 + 2048 * 8 + 1023) / 1024 * 1024; }
+    __host__ __device__ static int apl_off(int nt, int n, int k) {
+        return (bpl_bytes(nt, k) + 1023) / 1024 * 1024 + stg_bytes(n) + tab_bytes(n);
+    }
     __host__ __device__ static int raw_off(int nt, int n, int k) { return apl_off(nt, n, k) + SK_PL * APL_STAGE; }
     __host__ static int raw_stages(int nt, int n, int k) {
         int r = (BUDGET - TAIL - raw_off(nt, n, k)) / RAW_STAGE;
@@ -712,6 +717,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 
     const int SK_RAW = p.raw_stages;
     const int STG_OFF = (S::bpl_bytes(NT, p.K) + 1023) / 1024 * 1024;
+    const int POS_OFF = STG_OFF + S::stg_bytes(p.N), RUN_OFF = POS_OFF + (TC_BM * p.N * 2 + 15) / 16 * 16;
+    uint16_t* pos16 = reinterpret_cast<uint16_t*>(smem + POS_OFF);
+    int64_t* runbase = reinterpret_cast<int64_t*>(smem + RUN_OFF);
+    const int nruns = (TC_BM * p.N) >> p.run_shift;
+    const bool runs_in_smem = nruns <= 2048;
+    // bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks
+    // stay conflict free) that spreads ranks which differ by a power-of-two stride over all banks (the writes)
+    auto swz = [](uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); };
     const int APL_OFF = S::apl_off(NT, p.N, p.K), RAW_OFF = S::raw_off(NT, p.N, p.K);
     const int BAR_OFF = RAW_OFF + SK_RAW * S::RAW_STAGE;
     const uint32_t bar0 = smem_u32(smem + BAR_OFF);
@@ -742,6 +755,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         }
         split_store(smem + kb * B_PLANE_KB, (int)b_plane, (int)row, (int)kc, v, p.conjB);
     }
+    for (int i = tid; i < TC_BM * p.N; i += SK_THREADS) pos16[i] = (uint16_t)swz((uint32_t)p.pos[i]);
+    if (runs_in_smem)
+        for (int i = tid; i < nruns; i += SK_THREADS) runbase[i] = p.rel[(int64_t)i << p.run_shift];
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -785,7 +801,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             mbar_wait(accfull_bar(set), (i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
-            const int64_t* prow = p.pos + (int64_t)row * p.N;
+            const uint16_t* prow = pos16 + row * p.N;
 #pragma unroll 1
             for (int c0 = 0; c0 < NT; c0 += 16) {
                 uint32_t re[16], im[16];
@@ -801,10 +817,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: next-next tile may start
             asm volatile("bar.sync 1, 128;" ::: "memory");           // staging tile complete (epilogue warps only)
             float2* base = p.C + p.hi[t];
+            const int rmask = (1 << p.run_shift) - 1;
+#pragma unroll 4
             for (int j = etid; j < cnt; j += 128) {
-                float2 v = stg[j];
+                float2 v = stg[swz((uint32_t)j)];
                 float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
-                float2* dst = base + (p.contig ? (p.rel[0] + j) : p.rel[j]);
+                const int run = j >> p.run_shift;
+                float2* dst = base + (runs_in_smem ? runbase[run] : p.rel[(int64_t)run << p.run_shift]) + (j & rmask);
                 if (has_beta) {
                     float2 old = *dst;
                     o.x += br * old.x - bi * old.y;
@@ -970,6 +989,8 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
     a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
     a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.contig = e.contig; a.conjA = e.conjA; a.conjB = e.conjB;
     a.bn = e.bn; a.bk = e.bk; a.hi = e.hi; a.rel = e.rel; a.pos = e.pos;
+    a.run_shift = 0;
+    while ((1 << (a.run_shift + 1)) <= e.run) a.run_shift++;
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
     if (e.N <= 16) return launch_stem_tc<16>(ctx, a);

@@ -263,6 +263,18 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
             S.st_pos[(size_t)addr[(size_t)j].second] = j;
             if (addr[(size_t)j].first != addr[0].first + j) contig = false;
         }
+        // contiguous runs: largest power-of-two R with rel[j] == rel[j - j%R] + j%R for all j  (R = cnt when contig)
+        int64_t R = 1;
+        while (R * 2 <= cnt && cnt % (R * 2) == 0) {
+            const int64_t R2 = R * 2;
+            bool ok = true;
+            for (int64_t j = 0; j < cnt && ok; j += R2)
+                for (int64_t o = R; o < R2; o++)
+                    if (S.st_rel[(size_t)(j + o)] != S.st_rel[(size_t)j] + o) { ok = false; break; }
+            if (!ok) break;
+            R = R2;
+        }
+        S.st_run = (int32_t)R;
         S.st_hi = cb.hi;
         S.st_ok = true; S.st_swap = sw != 0; S.st_tm = (int32_t)TM; S.st_contig = contig;
     }

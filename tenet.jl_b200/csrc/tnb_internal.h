@@ -73,7 +73,7 @@ struct StepSpec {
     bool b_nmajor = false;
     // streaming "stem" kernel (huge dense operand x tiny operand): tile-invariant sorted output pattern
     bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
-    int32_t st_tm = 0;
+    int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
     int32_t tc_nt = 0;       // tcgen05 kernel: N tile (256/128), 0 = not used
@@ -149,6 +149,7 @@ struct StemArgs {
     void* C;
     int64_t M, lda;
     int32_t N, K, TM, contig, conjA, conjB;
+    int32_t run;              // contiguous run length of the sorted pattern (power of two): rel[j] = rel[j & ~(run-1)] + (j & (run-1))
     TabRef bn, bk;
     const int64_t* hi;        // [M/TM] tile base offsets in C
     const int64_t* rel;       // [TM*N] ascending offsets inside a tile
