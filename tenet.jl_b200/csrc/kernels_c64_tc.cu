@@ -755,7 +755,11 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         }
         split_store(smem + kb * B_PLANE_KB, (int)b_plane, (int)row, (int)kc, v, p.conjB);
     }
-    for (int i = tid; i < TC_BM * p.N; i += SK_THREADS) pos16[i] = (uint16_t)swz((uint32_t)p.pos[i]);
+    // rank table transposed to [col][row]: the 32 lanes of an epilogue warp (consecutive rows) read consecutive entries
+    for (int i = tid; i < TC_BM * p.N; i += SK_THREADS) {
+        const int row = i / p.N, col = i - row * p.N;
+        pos16[col * TC_BM + row] = (uint16_t)swz((uint32_t)p.pos[i]);
+    }
     if (runs_in_smem)
         for (int i = tid; i < nruns; i += SK_THREADS) runbase[i] = p.rel[(int64_t)i << p.run_shift];
     fence_proxy_async_smem();
@@ -801,7 +805,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             mbar_wait(accfull_bar(set), (i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
-            const uint16_t* prow = pos16 + row * p.N;
+            const uint16_t* prow = pos16 + row;
 #pragma unroll 1
             for (int c0 = 0; c0 < NT; c0 += 16) {
                 uint32_t re[16], im[16];
@@ -810,7 +814,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; j++)
-                    if (c0 + j < p.N) stg[prow[c0 + j]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                    if (c0 + j < p.N) stg[prow[(c0 + j) * TC_BM]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
             }
             tc_fence_before();
             __syncwarp();

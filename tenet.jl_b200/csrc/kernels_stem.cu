@@ -64,7 +64,11 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
         if (p.conjB) v.y = -v.y;
         Bs[k * N + n] = v;
     }
-    for (int i = tid; i < TM * N; i += (int)blockDim.x) pos16[i] = (uint16_t)p.pos[i];
+    // rank table transposed to [n][ml] (conflict-free for consecutive ml) and run bases of the sorted pattern
+    for (int i = tid; i < TM * N; i += (int)blockDim.x) {
+        const int ml = i / N, n = i - ml * N;
+        pos16[n * TM + ml] = (uint16_t)p.pos[i];
+    }
     __syncthreads();
 
     const E* __restrict__ A = reinterpret_cast<const E*>(p.A);
@@ -73,6 +77,9 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
     const bool unit_alpha = p.alpha[0] == 1.0 && p.alpha[1] == 0.0;
     const int64_t ntiles = p.M / TM;
     const int cnt = TM * N;
+    int run_shift = 0;
+    while ((1 << (run_shift + 1)) <= p.run) run_shift++;
+    const int rmask = (1 << run_shift) - 1;
     struct __align__(16) Vec { E v[VM]; };
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -105,12 +112,12 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
             for (int v = 0; v < VM; v++)
 #pragma unroll
                 for (int n = 0; n < NMAX; n++)
-                    if (n < N) tile[pos16[(ml + v) * N + n]] = acc[v][n];
+                    if (n < N) tile[pos16[n * TM + ml + v]] = acc[v][n];
         }
         __syncthreads();
         E* base = C + p.hi[t];
         for (int j = tid; j < cnt; j += (int)blockDim.x) {
-            E* dst = base + (p.contig ? (p.rel[0] + j) : p.rel[j]);
+            E* dst = base + p.rel[(int64_t)(j >> run_shift) << run_shift] + (j & rmask);
             E v = tile[j];
             if (!unit_alpha) v = cscale(p.alpha, v);
             if (has_beta) {
