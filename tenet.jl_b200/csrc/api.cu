@@ -145,9 +145,16 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         t.hi = dev_blob + S.st_hi_pos; t.rel = dev_blob + S.st_rel_pos; t.pos = dev_blob + S.st_pos_pos;
         t.alpha[0] = alpha[0]; t.alpha[1] = alpha[1]; t.beta[0] = beta[0]; t.beta[1] = beta[1];
         if (S.kernel == TNB_KERNEL_STEM) return tnb_launch_stem(ctx, dtype, t);
-        int rc = tnb_launch_c64_stem_tc(ctx, t);
-        if (rc != -1) return rc;
-        return tnb_launch_einsum_generic(ctx, dtype, a);          // misaligned big operand: exact-FP32 generic kernel
+        const int64_t cnt = (int64_t)S.st_tm * S.st_ncol;
+        for (int ps = 0; ps < S.st_npass; ps++) {
+            t.N = S.st_ncol; t.n0 = ps * S.st_ncol;
+            t.rel = dev_blob + S.st_rel_pos + ps * cnt; t.pos = dev_blob + S.st_pos_pos + ps * cnt;
+            int rc = tnb_launch_c64_stem_tc(ctx, t);
+            if (rc == -1 && ps == 0)
+                return tnb_launch_einsum_generic(ctx, dtype, a);  // misaligned big operand: exact-FP32 generic kernel
+            if (rc) return rc;
+        }
+        return TNB_OK;
     }
     if (S.kernel == TNB_KERNEL_C64_TF32) {
         int64_t lda = S.K > 1 ? S.ak.stride : S.M, ldb = S.K > 1 ? S.bk.stride : S.N;

@@ -673,7 +673,7 @@ struct StemTcArgs {
     const float2* B;          // small operand, gathered through bn/bk
     float2* C;
     int64_t M, lda;
-    int32_t N, K, contig, conjA, conjB;
+    int32_t N, K, n0, contig, conjA, conjB;
     int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
     int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
     TabRef bn, bk;
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const uint32_t k = kb * TC_BK + kc * 4 + i;
-            v[i] = (int)row < p.N ? p.B[tabc(p.bn, row) + tabc(p.bk, k)] : make_float2(0.f, 0.f);
+            v[i] = (int)row < p.N ? p.B[tabc(p.bn, p.n0 + row) + tabc(p.bk, k)] : make_float2(0.f, 0.f);
         }
         split_store(smem + kb * B_PLANE_KB, (int)b_plane, (int)row, (int)kc, v, p.conjB);
     }
@@ -991,7 +991,7 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
     if ((e.lda % 2) != 0 || ((uintptr_t)e.A % 16) != 0) return -1;
     StemTcArgs a;
     a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
-    a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.contig = e.contig; a.conjA = e.conjA; a.conjB = e.conjB;
+    a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.n0 = e.n0; a.contig = e.contig; a.conjA = e.conjA; a.conjB = e.conjB;
     a.bn = e.bn; a.bk = e.bk; a.hi = e.hi; a.rel = e.rel; a.pos = e.pos;
     a.run_shift = 0;
     while ((1 << (a.run_shift + 1)) <= e.run) a.run_shift++;

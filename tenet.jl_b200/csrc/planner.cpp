@@ -224,7 +224,11 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         const bool dense = sw ? S.b_nmajor : S.a_mmajor;
         if (S.L != 1 || !dense || Mb < 65536) continue;
         // class 1: SIMT streaming (N*K small: FP32 FMA keeps up with HBM); class 2: tensor-core stem (c64 only)
-        const bool tcst = cplx && elem_size == 8 && tnb_stem_tc_shape_ok(Mb, Ns, S.K);
+        // the tensor-core stem kernel takes <= 64 small-side columns per pass; wider small operands (<= 256) run as
+        // several passes that re-read the big operand (still far fewer bytes than a tile kernel without overlap)
+        const int64_t nper = Ns > 64 ? 64 : Ns;
+        const int64_t npass = Ns / std::max<int64_t>(nper, 1);
+        const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= 4 && tnb_stem_tc_shape_ok(Mb, nper, S.K);
         const bool simt = !tcst && Ns <= 16 && S.K <= 64;
         if (!simt && !tcst) continue;
         const int64_t lo_max = simt ? std::max<int64_t>(64, 4096 / std::max<int64_t>(Ns, 1)) : 128;
@@ -243,38 +247,47 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         HostTable cb;
         build_table(ext, st, &cb, lo_max);
         const int64_t TM = cb.lo_size;
-        if (TM < 64 || TM > 4096 || TM * Ns > 8192 || (TM % 2)) continue;
+        if (TM < 64 || TM > 4096 || TM * (simt ? Ns : nper) > 8192 || (TM % 2)) continue;
         if (!simt && TM != 128) continue;
         S.st_tc = !simt;
         std::vector<int64_t> ext2, st2;
         for (auto& e : small) { ext2.push_back(e.ext); st2.push_back(e.sc); }
         HostTable cs;
         build_table(ext2, st2, &cs);
-        const int64_t cnt = TM * Ns;
-        std::vector<std::pair<int64_t, int64_t>> addr((size_t)cnt);
-        for (int64_t ml = 0; ml < TM; ml++)
-            for (int64_t n = 0; n < Ns; n++) addr[(size_t)(ml * Ns + n)] = {cb.lo[(size_t)ml] + cs.at(n), ml * Ns + n};
-        std::sort(addr.begin(), addr.end());
-        S.st_rel.assign((size_t)cnt, 0);
-        S.st_pos.assign((size_t)cnt, 0);
+        const int64_t ncol = simt ? Ns : nper, passes = simt ? 1 : npass;
+        const int64_t cnt = TM * ncol;
+        S.st_rel.assign((size_t)(cnt * passes), 0);
+        S.st_pos.assign((size_t)(cnt * passes), 0);
         bool contig = true;
-        for (int64_t j = 0; j < cnt; j++) {
-            S.st_rel[(size_t)j] = addr[(size_t)j].first;
-            S.st_pos[(size_t)addr[(size_t)j].second] = j;
-            if (addr[(size_t)j].first != addr[0].first + j) contig = false;
-        }
-        // contiguous runs: largest power-of-two R with rel[j] == rel[j - j%R] + j%R for all j  (R = cnt when contig)
-        int64_t R = 1;
-        while (R * 2 <= cnt && cnt % (R * 2) == 0) {
-            const int64_t R2 = R * 2;
-            bool ok = true;
-            for (int64_t j = 0; j < cnt && ok; j += R2)
-                for (int64_t o = R; o < R2; o++)
-                    if (S.st_rel[(size_t)(j + o)] != S.st_rel[(size_t)j] + o) { ok = false; break; }
-            if (!ok) break;
-            R = R2;
+        int64_t R = cnt;
+        for (int64_t ps = 0; ps < passes; ps++) {
+            std::vector<std::pair<int64_t, int64_t>> addr((size_t)cnt);
+            for (int64_t ml = 0; ml < TM; ml++)
+                for (int64_t n = 0; n < ncol; n++)
+                    addr[(size_t)(ml * ncol + n)] = {cb.lo[(size_t)ml] + cs.at(ps * ncol + n), ml * ncol + n};
+            std::sort(addr.begin(), addr.end());
+            int64_t* rel = S.st_rel.data() + ps * cnt;
+            int64_t* pos = S.st_pos.data() + ps * cnt;
+            for (int64_t j = 0; j < cnt; j++) {
+                rel[j] = addr[(size_t)j].first;
+                pos[addr[(size_t)j].second] = j;
+                if (addr[(size_t)j].first != addr[0].first + j) contig = false;
+            }
+            // contiguous runs: largest power-of-two r with rel[j] == rel[j - j%r] + j%r for all j
+            int64_t r = 1;
+            while (r * 2 <= cnt && cnt % (r * 2) == 0) {
+                const int64_t r2 = r * 2;
+                bool ok = true;
+                for (int64_t j = 0; j < cnt && ok; j += r2)
+                    for (int64_t o = r; o < r2; o++)
+                        if (rel[j + o] != rel[j] + o) { ok = false; break; }
+                if (!ok) break;
+                r = r2;
+            }
+            R = std::min(R, r);
         }
         S.st_run = (int32_t)R;
+        S.st_npass = (int32_t)passes; S.st_ncol = (int32_t)ncol;
         S.st_hi = cb.hi;
         S.st_ok = true; S.st_swap = sw != 0; S.st_tm = (int32_t)TM; S.st_contig = contig;
     }

@@ -73,6 +73,7 @@ struct StepSpec {
     bool b_nmajor = false;
     // streaming "stem" kernel (huge dense operand x tiny operand): tile-invariant sorted output pattern
     bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
+    int32_t st_npass = 1, st_ncol = 0;   // passes over the small operand's columns, columns per pass
     int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
@@ -149,6 +150,7 @@ struct StemArgs {
     void* C;
     int64_t M, lda;
     int32_t N, K, TM, contig, conjA, conjB;
+    int32_t n0;               // first column of the small operand handled by this launch (multi-pass)
     int32_t run;              // contiguous run length of the sorted pattern (power of two): rel[j] = rel[j & ~(run-1)] + (j & (run-1))
     TabRef bn, bk;
     const int64_t* hi;        // [M/TM] tile base offsets in C
