@@ -347,6 +347,13 @@ def main():
             ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": None, "peak_basis": peak_src}
+        tr_file = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if a.workload == "sycamore53_m14" and os.path.exists(tr_file):
+            tr = json.load(open(tr_file)).get(name)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes"]
+                roofline["traffic_note"] = (f"ncu dram read+write of the largest launch of this kernel, {tr['launch']}: "
+                                            f"{tr['ratio']:.3f} x its algorithmic bytes (profiles/r1_traffic.json)")
         roofline.update({"kernel": name, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"],
                          "share_of_step": k["ms"] / max(sum(v["ms"] for v in by_kernel.values()), 1e-9),
                          "arithmetic_intensity": ai,
