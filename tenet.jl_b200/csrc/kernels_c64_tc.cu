@@ -738,8 +738,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     constexpr uint32_t TMEM_COLS = (4 * NT) < 32 ? 32 : 4 * NT;      // two sets of [re NT | im NT]
 
     if (tid == 0) {
-        for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 32); }
-        for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 32); mbar_init(apl_empty(s), 1); }
+        for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
+        for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -769,26 +769,33 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ---- workers: raw A tile -> planes ----
-        const int prow = tid & 127, pkc = tid >> 7;
-        const int raw_base = RAW_OFF + (pkc * 4 * TC_BM + prow) * 8;
-        int rs = 0, ps = 0;
-        uint32_t rphase = 0, pphase = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            for (uint32_t kb = 0; kb < nkb; kb++) {
-                mbar_wait(raw_full(rs), rphase);
-                float2 v[4];
-                const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+        // ---- workers: raw A tile -> planes.  Two groups of 4 warps take alternate k-blocks (group = parity of the
+        // global k-block counter = plane stage), so two latency chains (wait, LDS, split, STS, proxy fence, arrive)
+        // run concurrently; a thread owns one row and both 4-k halves of its k-block. ----
+        static_assert(SK_PL == 2, "one plane stage per worker group");
+        const int group = warp >> 2, prow = tid & 127;
+        const int raw_row = RAW_OFF + prow * 8;
+        int64_t my_tiles = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) my_tiles++;
+        const uint64_t total_kb = (uint64_t)my_tiles * nkb;
+        for (uint64_t g = group; g < total_kb; g += 2) {
+            const int rs = (int)(g % (uint64_t)SK_RAW);
+            const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g >> 1) & 1);
+            mbar_wait(raw_full(rs), rphase);
+            float2 v0[4], v1[4];
+            const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_row;
 #pragma unroll
-                for (int i = 0; i < 4; i++) v[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
-                mbar_wait(apl_empty(ps), pphase ^ 1);
-                split_store(smem + APL_OFF + ps * S::APL_STAGE, TC_BM * TC_BK * 4, prow, pkc, v, p.conjA);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
-                if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
-                if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
+            for (int i = 0; i < 4; i++) {
+                v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                v1[i] = *reinterpret_cast<const float2*>(raw + (4 + i) * TC_BM * 8);
             }
+            mbar_wait(apl_empty(group), pphase ^ 1);
+            uint8_t* pl = smem + APL_OFF + group * S::APL_STAGE;
+            split_store(pl, TC_BM * TC_BK * 4, prow, 0, v0, p.conjA);
+            split_store(pl, TC_BM * TC_BK * 4, prow, 1, v1, p.conjA);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(apl_full(group)); mbar_arrive(raw_empty(rs)); }
         }
     } else if (warp < 12) {
         // ---- epilogue warps: TMEM -> staging (rank order) -> C (ascending addresses) ----

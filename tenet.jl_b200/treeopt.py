@@ -18,6 +18,20 @@ from typing import Dict, List, Optional, Sequence, Tuple
 from .pathfinder import ContractionPath, _Net, _greedy_once, _logaddexp2, path_cost
 
 
+# "time" objective: a pairwise step costs max(MACs, BYTE_WEIGHT * elements moved) — on the B200 engine a complex64
+# element moved through HBM (8 B at ~3.3 TB/s achieved) costs as much time as ~73 complex MACs (8 flop at ~240 TFLOP/s).
+BYTE_WEIGHT_LOG2 = math.log2(73.0)
+
+
+def _step_cost(net, la_mask, lb_mask, lc_mask, minimize):
+    lm = net.lsize(la_mask | lb_mask)
+    if minimize != "time":
+        return lm
+    sa, sb, sc = net.lsize(la_mask), net.lsize(lb_mask), net.lsize(lc_mask)
+    moved = _logaddexp2(_logaddexp2(sa, sb), sc) + BYTE_WEIGHT_LOG2
+    return max(lm, moved)
+
+
 def _popbits(mask: int):
     while mask:
         low = mask & -mask
@@ -129,10 +143,10 @@ def _dp_optimal(tree: _Tree, items: List[int], minimize: str):
             S1 = S ^ S2
             if S2 and S1:
                 c1, c2 = best[S1], best[S2]
-                step = net.lsize(legs[S1] | legs[S2])
+                step = _step_cost(net, legs[S1], legs[S2], legs[S], minimize)
                 cost = _logaddexp2(_logaddexp2(c1[0], c2[0]), step)
                 size = max(c1[1], c2[1], lsz[S])
-                key = (cost, size) if minimize == "flops" else (max(size, 0.0), cost)
+                key = (cost, size) if minimize in ("flops", "time") else (max(size, 0.0), cost)
                 if bc is None or key < bc[0]:
                     bc = (key, cost, size, (c1[2], c2[2]))
             if S2 == 0:
@@ -142,18 +156,19 @@ def _dp_optimal(tree: _Tree, items: List[int], minimize: str):
     return best[full]
 
 
-def _current_cost(tree: _Tree, node: int, frontier: set):
+def _current_cost(tree: _Tree, node: int, frontier: set, minimize: str = "flops"):
     """cost / peak size of the part of the tree between `node` and the frontier"""
     net = tree.net
     if node in frontier:
         return -1e9, 0.0
     l, r = tree.children[node]
-    cl, sl = _current_cost(tree, l, frontier)
-    cr, sr = _current_cost(tree, r, frontier)
+    cl, sl = _current_cost(tree, l, frontier, minimize)
+    cr, sr = _current_cost(tree, r, frontier, minimize)
     ll = tree.legs(tree.sub_counts(l))
     lr = tree.legs(tree.sub_counts(r))
-    step = net.lsize(ll | lr)
-    out = net.lsize(tree.legs(tree.sub_counts(node)))
+    lo = tree.legs(tree.sub_counts(node))
+    step = _step_cost(net, ll, lr, lo, minimize)
+    out = net.lsize(lo)
     return _logaddexp2(_logaddexp2(cl, cr), step), max(sl, sr, out)
 
 
@@ -181,10 +196,10 @@ def subtree_reconfigure(net: _Net, steps, removed: int = 0, size: int = 8, round
             if len(frontier) < 3:
                 continue
             fs = set(frontier)
-            cur_c, cur_s = _current_cost(tree, node, fs)
+            cur_c, cur_s = _current_cost(tree, node, fs, minimize)
             new_c, new_s, order = _dp_optimal(tree, frontier, minimize)
-            better = (new_c < cur_c - 1e-9) if minimize == "flops" else ((new_s, new_c) < (cur_s - 1e-9, cur_c))
-            if minimize == "flops" and new_c <= cur_c + 1e-9 and new_s < cur_s - 1e-9:
+            better = (new_c < cur_c - 1e-9) if minimize in ("flops", "time") else ((new_s, new_c) < (cur_s - 1e-9, cur_c))
+            if minimize in ("flops", "time") and new_c <= cur_c + 1e-9 and new_s < cur_s - 1e-9:
                 better = True
             if not better:
                 continue
@@ -216,8 +231,19 @@ def subtree_reconfigure(net: _Net, steps, removed: int = 0, size: int = 8, round
     return tree.ssa()
 
 
+def tree_time_cost(net: _Net, steps, removed: int = 0) -> float:
+    """log2 of sum over steps of max(MACs, BYTE_WEIGHT * elements moved) — per slice"""
+    tree = _Tree(net, steps, removed)
+    tot = -1e9
+    for node, (l, r) in tree.children.items():
+        ll = tree.legs(tree.sub_counts(l)); lr = tree.legs(tree.sub_counts(r)); lo = tree.legs(tree.sub_counts(node))
+        tot = _logaddexp2(tot, _step_cost(net, ll, lr, lo, "time"))
+    return tot
+
+
 def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, target_log2_size: Optional[float] = None,
-                 reconf_size: int = 8, reconf_rounds: int = 2, keep: int = 4, verbose: bool = False) -> ContractionPath:
+                 reconf_size: int = 8, reconf_rounds: int = 2, keep: int = 4, verbose: bool = False,
+                 minimize: str = "flops") -> ContractionPath:
     """Randomised greedy restarts -> subtree reconfiguration of the best few -> greedy slicing with
     reconfiguration of the sliced tree.  Returns the best (total MACs over all slices) path found."""
     from .pathfinder import find_slices
@@ -233,7 +259,7 @@ def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, tar
     cands.sort(key=lambda c: (c[0], c[1]))
     best = None
     for lm, ls, steps in cands[:keep]:
-        s2 = subtree_reconfigure(net, steps, 0, reconf_size, reconf_rounds, "flops", rng)
+        s2 = subtree_reconfigure(net, steps, 0, reconf_size, reconf_rounds, minimize, rng)
         lm2, ls2, _ = path_cost(net, s2, 0)
         if verbose:
             print(f"  greedy 2^{lm:.2f}/2^{ls:.0f} -> reconf 2^{lm2:.2f}/2^{ls2:.0f}")
@@ -241,15 +267,23 @@ def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, tar
         if target_log2_size is not None and ls2 > target_log2_size:
             p = find_slices(inputs, sizes, output, p, target_log2_size)
             removed = sum(1 << net.bit[i] for i in p.sliced)
-            s3 = subtree_reconfigure(net, p.steps, removed, reconf_size, reconf_rounds, "flops", rng)
+            s3 = subtree_reconfigure(net, p.steps, removed, reconf_size, reconf_rounds, minimize, rng)
             lm3, ls3, _ = path_cost(net, s3, removed)
-            if ls3 <= target_log2_size + 1e-9 and lm3 < p.log2_macs:
+            ok3 = lm3 < p.log2_macs if minimize != "time" else tree_time_cost(net, s3, removed) < tree_time_cost(net, p.steps, removed)
+            if ls3 <= target_log2_size + 1e-9 and ok3:
                 p = ContractionPath(s3, p.sliced, tuple(output), lm3, ls3, p.nslices, {})
             if verbose:
                 print(f"    sliced x2^{math.log2(p.nslices):.0f}: per-slice 2^{p.log2_macs:.2f}, total 2^{p.log2_macs + math.log2(p.nslices):.2f}")
-        total = p.log2_macs + math.log2(p.nslices)
+        if minimize == "time":
+            removed = sum(1 << net.bit[i] for i in p.sliced)
+            total = tree_time_cost(net, p.steps, removed) + math.log2(p.nslices)
+            if verbose:
+                print(f"    time-model cost 2^{total:.2f} MAC-equivalents")
+        else:
+            total = p.log2_macs + math.log2(p.nslices)
         if best is None or total < best[0]:
             best = (total, p)
     p = best[1]
-    p.info = {"method": "greedy+subtree-reconf", "trials": ntrials, "reconf_size": reconf_size, "seed": seed}
+    p.info = {"method": "greedy+subtree-reconf", "trials": ntrials, "reconf_size": reconf_size, "seed": seed,
+              "minimize": minimize, "score_log2": best[0]}
     return p

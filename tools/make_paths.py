@@ -50,7 +50,7 @@ def main():
     if a.method == "hyper":
         from tenet_jl_b200 import treeopt
         p = treeopt.hyper_search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
-                                 reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True)
+                                 reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True, minimize=a.minimize)
     else:
         p = tb.pathfinder.search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
                                  minimize=a.minimize)
