@@ -663,7 +663,8 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 // Chain length in TMEM is 6*K/8 <= 96 MMAs (K <= 128): the round-toward-zero bias stays ~6e-6 relative.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SK_WORKERS = 256;                 // warps 0-7
-constexpr int SK_THREADS = SK_WORKERS + 128 + 64;   // + epilogue warps 8-11, MMA warp 12, copy warp 13
+constexpr int SK_EPI = 256;                     // warps 8-15: two per TMEM lane quarter, each takes half of the columns
+constexpr int SK_THREADS = SK_WORKERS + SK_EPI + 64;   // + MMA warp 16, copy warp 17
 constexpr int SK_PL = 2;                        // A plane stages (16 KB each)
 constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as many as shared memory allows — the
                                                 // bytes in flight per SM (>= 64 KB) are what saturates HBM
@@ -740,10 +741,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     if (tid == 0) {
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
         for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 16) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     // small operand -> resident planes (all k-blocks): plane q at q*b_plane, k-block kb at kb*B_PLANE_KB
     for (uint32_t u = tid; u < (uint32_t)NT * nkb * 2; u += SK_THREADS) {
         const uint32_t row = u % NT, r = u / NT, kc = r & 1, kb = r >> 1;
@@ -797,40 +798,45 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             __syncwarp();
             if (lane == 0) { mbar_arrive(apl_full(group)); mbar_arrive(raw_empty(rs)); }
         }
-    } else if (warp < 12) {
+    } else if (warp < 16) {
         // ---- epilogue warps: TMEM -> staging (rank order) -> C (ascending addresses) ----
-        const int q = warp & 3;
-        const int etid = tid - SK_WORKERS;                         // 0..127
+        const int q = warp & 3, half = (warp - 8) >> 2;
+        const int etid = tid - SK_WORKERS;                         // 0..255
         const uint32_t row = q * 32 + lane;
         float2* stg = reinterpret_cast<float2*>(smem + STG_OFF);
         const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
         const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
         const int cnt = TC_BM * p.N;
+        constexpr int COLS = NT >= 32 ? NT / 2 : NT;               // columns per warp (NT = 16: warps of half 1 skip the drain)
+        const int cbeg = NT >= 32 ? half * COLS : 0;
+        const bool drains = NT >= 32 || half == 0;
         uint32_t i = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
             const uint32_t set = i & 1;
             mbar_wait(accfull_bar(set), (i >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
-            const uint16_t* prow = pos16 + row;
+            if (drains) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
+                const uint16_t* prow = pos16 + row;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 16) {
-                uint32_t re[16], im[16];
-                tmem_ld16(taddr + c0, re);
-                tmem_ld16(taddr + NT + c0, im);
-                tmem_ld_wait();
+                for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 16) {
+                    uint32_t re[16], im[16];
+                    tmem_ld16(taddr + c0, re);
+                    tmem_ld16(taddr + NT + c0, im);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (c0 + j < p.N) stg[prow[(c0 + j) * TC_BM]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                    for (int j = 0; j < 16; j++)
+                        if (c0 + j < p.N) stg[prow[(c0 + j) * TC_BM]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: next-next tile may start
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // staging tile complete (epilogue warps only)
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile complete (epilogue warps only)
             float2* base = p.C + p.hi[t];
             const int rmask = (1 << p.run_shift) - 1;
 #pragma unroll 4
-            for (int j = etid; j < cnt; j += 128) {
+            for (int j = etid; j < cnt; j += SK_EPI) {
                 float2 v = stg[swz((uint32_t)j)];
                 float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
                 const int run = j >> p.run_shift;
@@ -842,9 +848,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 }
                 *dst = o;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // staging tile free again
+            asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile free again
         }
-    } else if (warp == 12) {
+    } else if (warp == 16) {
         // ---- MMA issuer ----
         if (lane == 0) {
             constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
@@ -905,7 +911,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == 16) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
