@@ -218,7 +218,11 @@ def main():
         S = max(1, int(15e12 / max(flops_slice, 1.0)))
     S = max(1, min(S, max(1, nslices // max(world, 1))))
 
+    replicas = nslices == 1       # un-sliced network: nothing to shard -> N independent replicas, no collective
+
     def step_range(i):
+        if replicas:
+            return 0, 1, 1
         base = (i * world * S) % max(nslices - world * S + 1, 1)
         return base + rank, world, base + world * S
 
@@ -231,7 +235,7 @@ def main():
         plan.zero_output()
         b, s, e = step_range(i)
         plan.execute(b, s, e, accumulate=True)
-        if world > 1:
+        if world > 1 and not replicas:
             tb.distributed.allreduce_sum(ctx, plan.out_array)
         if e2e:
             return plan.out_array.to_numpy()
@@ -380,7 +384,8 @@ def main():
                    "steps_per_slice": info["nsteps_per_slice"], "peak_intermediate_bytes": info["max_intermediate_elems"] * dtype.itemsize,
                    "workspace_bytes": info["workspace_bytes"],
                    "l2": "intermediates (>= hundreds of MB per slice) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": f"slices round-robin over {world} GPU(s), one all-reduce per step" if world > 1 else "single GPU"},
+                   "parallelism": ("single GPU" if world == 1 else f"{world} independent replicas (un-sliced network, no collective)"
+                                   if replicas else f"slices round-robin over {world} GPU(s), one all-reduce per step")},
         "slices_per_s": total_slices / (ms * 1e-3), "slices_per_s_per_gpu": total_slices / (ms * 1e-3) / world,
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / a.steps, "result_checksum": [float(np.real(res).sum()), float(np.imag(res).sum())] if res is not None else None},

@@ -1,25 +1,23 @@
-// kernels_c64_tc.cu — ComplexF32 GEMM-shaped steps on the 5th-gen tensor cores (tcgen05 + TMEM), 3xTF32 split.
+// kernels_c64_tc.cu — ComplexF32 steps on the 5th-gen tensor cores (tcgen05 + TMEM), 3xTF32 split.
 //
-// What it replaces: the BLAS cgemm behind Muscle.binary_einsum for the large steps of a contraction path
-// (/root/reference/src/Operations/overlap.jl:12 -> contract -> binary_einsum).
+// What it replaces: the BLAS cgemm (plus the permutedims passes around it) behind Muscle.binary_einsum for the large
+// steps of a contraction path (/root/reference/src/Operations/overlap.jl:12 -> contract -> binary_einsum).
 //
 //   C[m,n] = sum_k A[m,k] * B[n,k]        A: M-fastest dense [K][M], B: N-fastest dense [K][N]  (planner layouts)
 //
-// Complex product from real sub-GEMMs:  Cre = Are.Bre - Aim.Bim,  Cim = Are.Bim + Aim.Bre.
-// Each real product a*b is evaluated as  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi  with x_hi = tf32(x), x_lo = x - x_hi,
-// i.e. 12 tcgen05.mma.kind::tf32 per 8 complex k per tile, accumulating in fp32 in TMEM.  The relative error of a
-// product is ~2^-21 (the dropped a_lo*b_lo term and the truncation of x_lo to TF32), so results match an FP32
-// cgemm to a few 1e-7 * sqrt(K) — the stated bound for this mode (tests/test_gpu_tc.py).
+// Complex product from real sub-GEMMs:  Cre = Are.Bre - Aim.Bim,  Cim = Are.Bim + Aim.Bre  (minus sign = a_negate bit).
+// Each real product a*b is evaluated as  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi  with x_hi = x & 0xffffe000 (what the
+// tensor core reads anyway), x_lo = x - x_hi (exact): 12 tcgen05.mma.kind::tf32 per 8 complex k per tile, FP32
+// accumulation in TMEM.  Operands are staged raw by cp.async.bulk, split into four planes per operand (re_hi, re_lo,
+// im_hi, im_lo) in the UMMA K-major no-swizzle core-matrix layout by worker warps; the permuted / split operand never
+// exists in global memory.
 //
-// Structure (one CTA per 128 x NT output tile, 288 threads):
-//   warps 0-7  producers: ld.global (coalesced along m/n, 8 B per lane) -> de-interleave re/im, split hi/lo in
-//              registers -> st.shared.v4 into four planes per operand in the UMMA K-major no-swizzle core-matrix
-//              layout -> fence.proxy.async -> mbarrier arrive (full[stage]).  The permuted/split operand is never
-//              written to global memory.
-//   warp 8     one elected thread issues the 12 MMAs per stage (a_negate does the minus sign), tcgen05.commit
-//              frees the stage (empty[stage]) and finally signals the accumulator (acc_full).
-//   warps 0-7  epilogue: tcgen05.ld (32x32b.x16) the two accumulators (Cre: TMEM cols [0,NT), Cim: [NT,2NT)),
-//              alpha/beta, scatter into the consumer's layout through the cm/cn offset tables.
+// Three kernels share these pieces:
+//   c64_tf32x3_kernel<NT>      "fast mode": 128 x NT tile, whole K chained in TMEM (error grows with K), register prefetch
+//   c64_tf32x3_acc_kernel      default GEMM kernel: 128 x 128 tile, bulk-copy raw ring, TMEM chunks of 64 k drained into
+//                              round-to-nearest FP32 totals, ragged edges, split-K
+//   c64_tf32x3_stem_kernel<NT> persistent HBM-bound kernel for huge x small steps (small operand resident as planes,
+//                              sorted-pattern coalesced epilogue overlapped with the next tile)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tnb_internal.h"
