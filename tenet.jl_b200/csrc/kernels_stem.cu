@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
         const int ml = i / N, n = i - ml * N;
         pos16[n * TM + ml] = (uint16_t)p.pos[i];
     }
+    int run_shift = 0;
+    while ((1 << (run_shift + 1)) <= p.run) run_shift++;
+    const int rmask = (1 << run_shift) - 1;
+    const int nruns = (TM * N) >> run_shift;
+    int64_t* runbase = reinterpret_cast<int64_t*>(pos16 + ((TM * N + 3) & ~3));     // [nruns] (launcher sized smem for it)
+    for (int i = tid; i < nruns; i += (int)blockDim.x) runbase[i] = p.rel[(int64_t)i << run_shift];
     __syncthreads();
 
     const E* __restrict__ A = reinterpret_cast<const E*>(p.A);
@@ -77,9 +83,6 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
     const bool unit_alpha = p.alpha[0] == 1.0 && p.alpha[1] == 0.0;
     const int64_t ntiles = p.M / TM;
     const int cnt = TM * N;
-    int run_shift = 0;
-    while ((1 << (run_shift + 1)) <= p.run) run_shift++;
-    const int rmask = (1 << run_shift) - 1;
     struct __align__(16) Vec { E v[VM]; };
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
         __syncthreads();
         E* base = C + p.hi[t];
         for (int j = tid; j < cnt; j += (int)blockDim.x) {
-            E* dst = base + p.rel[(int64_t)(j >> run_shift) << run_shift] + (j & rmask);
+            E* dst = base + runbase[j >> run_shift] + (j & rmask);
             E v = tile[j];
             if (!unit_alpha) v = cscale(p.alpha, v);
             if (has_beta) {
@@ -133,7 +136,9 @@ __global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
 template <typename E, int VM>
 int launch(tnb_ctx* ctx, const StemArgs& a) {
     const size_t esz = sizeof(E);
-    const size_t smem = (((size_t)a.K * a.N + 1) & ~(size_t)1) * esz + (size_t)a.TM * a.N * esz + (size_t)a.TM * a.N * 2;
+    const size_t cnt = (size_t)a.TM * a.N;
+    const size_t smem = (((size_t)a.K * a.N + 1) & ~(size_t)1) * esz + cnt * esz + ((cnt + 3) & ~(size_t)3) * 2 +
+                        (cnt / (size_t)(a.run > 0 ? a.run : 1) + 1) * 8;
     const int64_t ntiles = a.M / a.TM;
     // every thread owns VM consecutive m of a tile: no idle lanes in the compute phase
     int threads = (int)(a.TM / VM);
@@ -142,7 +147,7 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
     int64_t per_sm = smem > 0 ? (int64_t)(200 * 1024 / smem) : 8;
     const int64_t by_threads = 2048 / threads;
     if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->sm_count * per_sm;
     if (grid > ntiles) grid = ntiles;

@@ -231,7 +231,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= 4 && tnb_stem_tc_shape_ok(Mb, nper, S.K);
         const bool simt = !tcst && Ns <= 16 && S.K <= 64;
         if (!simt && !tcst) continue;
-        const int64_t lo_max = simt ? std::max<int64_t>(64, 4096 / std::max<int64_t>(Ns, 1)) : 128;
+        const int64_t lo_max = simt ? std::max<int64_t>(64, 2048 / std::max<int64_t>(Ns, 1)) : 128;
         std::vector<int64_t> ext, st;
         for (auto& e : big) {
             // a single mode longer than a tile is split (d, ext/d) with d the largest divisor that fits
