@@ -663,7 +663,7 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 constexpr int SK_WORKERS = 256;                 // warps 0-7
 constexpr int SK_EPI = 256;                     // warps 8-15: two per TMEM lane quarter, each takes half of the columns
 constexpr int SK_THREADS = SK_WORKERS + SK_EPI + 64;   // + MMA warp 16, copy warp 17
-constexpr int SK_PL = 2;                        // A plane stages (16 KB each)
+constexpr int SK_PL_MAX = 4;                    // A plane stages (16 KB each): 4 when the smem budget allows, else 2
 constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as many as shared memory allows — the
                                                 // bytes in flight per SM (>= 64 KB) are what saturates HBM
 
@@ -674,6 +674,7 @@ struct StemTcArgs {
     int64_t M, lda;
     int32_t N, K, n0, contig, conjA, conjB;
     int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
+    int32_t pl_stages;        // 2 or 4 A-plane stages
     int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
@@ -686,22 +687,23 @@ struct StemTcArgs {
 struct SkSmem {
     static constexpr int RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
     static constexpr int APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
-    static constexpr int NBARS = 2 * SK_RAW_MAX + 2 * SK_PL + 4;
+    static constexpr int NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4;
     static constexpr int TAIL = NBARS * 8 + 16;
     static constexpr int BUDGET = 227 * 1024;
     __host__ __device__ static int bpl_bytes(int nt, int k) { return 4 * (k / TC_BK) * nt * TC_BK * 4; }
     __host__ __device__ static int stg_bytes(int n) { return (TC_BM * n * 8 + 1023) / 1024 * 1024; }
-    // after the staging tile: pos16[128*N] (rank of every (row, col), bank-swizzled) and up to 2048 run bases (int64)
-    __host__ __device__ static int tab_bytes(int n) { return (TC_BM * n * 2 + 2048 * 8 + 1023) / 1024 * 1024; }
+    // after the staging tile: pos16[128*N] (rank of every (row, col), bank-swizzled) and up to 512 run bases (int64)
+    static constexpr int RUNS_MAX = 512;
+    __host__ __device__ static int tab_bytes(int n) { return (TC_BM * n * 2 + RUNS_MAX * 8 + 1023) / 1024 * 1024; }
     __host__ __device__ static int apl_off(int nt, int n, int k) {
         return (bpl_bytes(nt, k) + 1023) / 1024 * 1024 + stg_bytes(n) + tab_bytes(n);
     }
-    __host__ __device__ static int raw_off(int nt, int n, int k) { return apl_off(nt, n, k) + SK_PL * APL_STAGE; }
-    __host__ static int raw_stages(int nt, int n, int k) {
-        int r = (BUDGET - TAIL - raw_off(nt, n, k)) / RAW_STAGE;
+    __host__ __device__ static int raw_off(int nt, int n, int k, int pl) { return apl_off(nt, n, k) + pl * APL_STAGE; }
+    __host__ static int raw_stages(int nt, int n, int k, int pl) {
+        int r = (BUDGET - TAIL - raw_off(nt, n, k, pl)) / RAW_STAGE;
         return r > SK_RAW_MAX ? SK_RAW_MAX : r;
     }
-    __host__ __device__ static int total(int nt, int n, int k, int raw) { return raw_off(nt, n, k) + raw * RAW_STAGE + TAIL; }
+    __host__ __device__ static int total(int nt, int n, int k, int pl, int raw) { return raw_off(nt, n, k, pl) + raw * RAW_STAGE + TAIL; }
 };
 
 template <int NT>   // UMMA N (16, 32, 64)
@@ -720,19 +722,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     uint16_t* pos16 = reinterpret_cast<uint16_t*>(smem + POS_OFF);
     int64_t* runbase = reinterpret_cast<int64_t*>(smem + RUN_OFF);
     const int nruns = (TC_BM * p.N) >> p.run_shift;
-    const bool runs_in_smem = nruns <= 2048;
+    const bool runs_in_smem = nruns <= S::RUNS_MAX;
     // bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks
     // stay conflict free) that spreads ranks which differ by a power-of-two stride over all banks (the writes)
     auto swz = [](uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); };
-    const int APL_OFF = S::apl_off(NT, p.N, p.K), RAW_OFF = S::raw_off(NT, p.N, p.K);
+    const int SK_PL = p.pl_stages;
+    const int APL_OFF = S::apl_off(NT, p.N, p.K), RAW_OFF = S::raw_off(NT, p.N, p.K, SK_PL);
     const int BAR_OFF = RAW_OFF + SK_RAW * S::RAW_STAGE;
     const uint32_t bar0 = smem_u32(smem + BAR_OFF);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (SK_RAW_MAX + s); };
     auto apl_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + s); };
-    auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + SK_PL + s); };
-    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL + s); };
-    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL + 2 + s); };
+    auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + SK_PL_MAX + s); };
+    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + s); };
+    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 2 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + S::NBARS * 8);
     constexpr uint32_t TMEM_COLS = (4 * NT) < 32 ? 32 : 4 * NT;      // two sets of [re NT | im NT]
 
@@ -771,7 +774,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         // ---- workers: raw A tile -> planes.  Two groups of 4 warps take alternate k-blocks (group = parity of the
         // global k-block counter = plane stage), so two latency chains (wait, LDS, split, STS, proxy fence, arrive)
         // run concurrently; a thread owns one row and both 4-k halves of its k-block. ----
-        static_assert(SK_PL == 2, "one plane stage per worker group");
         const int group = warp >> 2, prow = tid & 127;
         const int raw_row = RAW_OFF + prow * 8;
         int64_t my_tiles = 0;
@@ -779,7 +781,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         const uint64_t total_kb = (uint64_t)my_tiles * nkb;
         for (uint64_t g = group; g < total_kb; g += 2) {
             const int rs = (int)(g % (uint64_t)SK_RAW);
-            const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g >> 1) & 1);
+            const int ps = (int)(g % (uint64_t)SK_PL);          // group g%2 owns stages {group, group+2}
+            const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g / (uint64_t)SK_PL) & 1);
             mbar_wait(raw_full(rs), rphase);
             float2 v0[4], v1[4];
             const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_row;
@@ -788,13 +791,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
                 v1[i] = *reinterpret_cast<const float2*>(raw + (4 + i) * TC_BM * 8);
             }
-            mbar_wait(apl_empty(group), pphase ^ 1);
-            uint8_t* pl = smem + APL_OFF + group * S::APL_STAGE;
+            mbar_wait(apl_empty(ps), pphase ^ 1);
+            uint8_t* pl = smem + APL_OFF + ps * S::APL_STAGE;
             split_store(pl, TC_BM * TC_BK * 4, prow, 0, v0, p.conjA);
             split_store(pl, TC_BM * TC_BK * 4, prow, 1, v1, p.conjA);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(apl_full(group)); mbar_arrive(raw_empty(rs)); }
+            if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
         }
     } else if (warp < 16) {
         // ---- epilogue warps: TMEM -> staging (rank order) -> C (ascending addresses) ----
@@ -917,9 +920,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 
 template <int NT>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
-    a.raw_stages = SkSmem::raw_stages(NT, a.N, a.K);
+    // four plane stages (a worker group refills one while the tensor core reads its other one) if that still leaves
+    // >= 5 raw stages (40 KB of bulk copies in flight), else two
+    a.pl_stages = SkSmem::raw_stages(NT, a.N, a.K, 4) >= 5 ? 4 : 2;
+    a.raw_stages = SkSmem::raw_stages(NT, a.N, a.K, a.pl_stages);
     if (a.raw_stages < 3) return -1;
-    const int smem = SkSmem::total(NT, a.N, a.K, a.raw_stages);
+    const int smem = SkSmem::total(NT, a.N, a.K, a.pl_stages, a.raw_stages);
     TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
