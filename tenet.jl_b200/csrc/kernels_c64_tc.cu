@@ -650,32 +650,47 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 // the kernel is organised around HBM, not around the tensor pipe:
 //   * one persistent CTA per SM walks 128-row tiles of the big operand; its A tile rows arrive by cp.async.bulk
 //     (8 KB per 8 k) into a raw ring, every A byte is read from HBM exactly once;
-//   * the small operand is gathered, split (hi/lo, re/im) and laid out as UMMA planes ONCE per CTA for all of K
-//     (<= 64 KB) and stays resident;
-//   * 8 worker warps split the raw A tiles into planes, one thread issues 12 x kind::tf32 MMAs (N wide) per 8 k into
-//     one of two TMEM accumulator sets;
-//   * 4 epilogue warps drain the other set (tcgen05.ld), drop each value at the RANK of its output address inside
+//   * the small operand is gathered, split (hi/lo) and laid out ONCE per CTA for all of K as two resident UMMA
+//     planes P_hi, P_lo of 2N rows each: rows [0,N) hold B_re, rows [N,2N) hold B_im.  One MMA of width 2N then
+//     produces [X.B_re | X.B_im] for an A plane X, so a k-block costs 6 MMAs instead of 12 — a 128 x n x 8 tf32 MMA
+//     costs ~46 clk for every n <= 64 (the 4 KB A read from shared memory, measured by tools/probes/mma_probe.cu), so
+//     halving the MMA count halves the tensor-pipe time of the small-N steps:
+//         F = A_re.B  (A_rh.P_lo + A_rl.P_hi + A_rh.P_hi)        E = A_im.B  (A_ih.P_lo + A_il.P_hi + A_ih.P_hi)
+//         C_re = F[0:N] - E[N:2N]      C_im = F[N:2N] + E[0:N]     (combined by the epilogue warps in FP32)
+//   * 8 worker warps split the raw A tiles into planes, one thread issues the MMAs into one of two TMEM sets
+//     (4N columns each);
+//   * 8 epilogue warps drain the other set (tcgen05.ld), drop each value at the RANK of its output address inside
 //     the tile's (tile-invariant, planner-sorted) address pattern in a shared staging tile, and write the tile to C
-//     in ascending address order — coalesced whatever layout the consumer asked for.  Drain of tile i overlaps the
-//     copies, splits and MMAs of tile i+1.
-// Chain length in TMEM is 6*K/8 <= 96 MMAs (K <= 128): the round-toward-zero bias stays ~6e-6 relative.
+//     in ascending address order, two elements (16 B) per thread — coalesced whatever layout the consumer asked for.
+//     When the rank is additive, rank(row, col) = r(row) + c(col) (always the case for power-of-two extents), it is
+//     computed from one register and a broadcast column table instead of a per-element table lookup.
+//     Drain of tile i overlaps the copies, splits and MMAs of tile i+1.
+// Chain length in TMEM is 3*K/8 <= 48 MMAs per accumulator (K <= 128): the round-toward-zero bias stays ~3e-6 relative.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SK_WORKERS = 256;                 // warps 0-7
 constexpr int SK_EPI = 256;                     // warps 8-15: two per TMEM lane quarter, each takes half of the columns
 constexpr int SK_THREADS = SK_WORKERS + SK_EPI + 64;   // + MMA warp 16, copy warp 17
 constexpr int SK_PL_MAX = 4;                    // A plane stages (16 KB each): 4 when the smem budget allows, else 2
 constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as many as shared memory allows — the
-                                                // bytes in flight per SM (>= 64 KB) are what saturates HBM
+                                                // bytes in flight per SM (>= 40 KB) are what saturates HBM
+constexpr int SK_RUNS_MAX = 1024;               // run bases kept in shared memory (int32)
+constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
+constexpr int SK_APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
+constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4;
+constexpr int SK_BUDGET = 227 * 1024;
 
 struct StemTcArgs {
     const float2* A;          // dense [K][M]
     const float2* B;          // small operand, gathered through bn/bk
     float2* C;
     int64_t M, lda;
-    int32_t N, K, n0, contig, conjA, conjB;
+    int32_t N, K, n0, conjA, conjB;
     int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
     int32_t pl_stages;        // 2 or 4 A-plane stages
     int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
+    int32_t additive;         // pos[row*N + col] == pos[row*N] + pos[col] - pos[0]
+    int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
+    int32_t off_stg, off_tab, off_run, off_apl, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
     const int64_t* rel;       // [128*N]
@@ -683,61 +698,71 @@ struct StemTcArgs {
     float alpha[2], beta[2];
 };
 
-// shared-memory map (sizes depend on N, K): [ B planes | staging tile | A planes ring | raw ring | barriers | tmem slot ]
-struct SkSmem {
-    static constexpr int RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
-    static constexpr int APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
-    static constexpr int NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4;
-    static constexpr int TAIL = NBARS * 8 + 16;
-    static constexpr int BUDGET = 227 * 1024;
-    __host__ __device__ static int bpl_bytes(int nt, int k) { return 4 * (k / TC_BK) * nt * TC_BK * 4; }
-    __host__ __device__ static int stg_bytes(int n) { return (TC_BM * n * 8 + 1023) / 1024 * 1024; }
-    // after the staging tile: pos16[128*N] (rank of every (row, col), bank-swizzled) and up to 512 run bases (int64)
-    static constexpr int RUNS_MAX = 512;
-    __host__ __device__ static int tab_bytes(int n) { return (TC_BM * n * 2 + RUNS_MAX * 8 + 1023) / 1024 * 1024; }
-    __host__ __device__ static int apl_off(int nt, int n, int k) {
-        return (bpl_bytes(nt, k) + 1023) / 1024 * 1024 + stg_bytes(n) + tab_bytes(n);
-    }
-    __host__ __device__ static int raw_off(int nt, int n, int k, int pl) { return apl_off(nt, n, k) + pl * APL_STAGE; }
-    __host__ static int raw_stages(int nt, int n, int k, int pl) {
-        int r = (BUDGET - TAIL - raw_off(nt, n, k, pl)) / RAW_STAGE;
-        return r > SK_RAW_MAX ? SK_RAW_MAX : r;
-    }
-    __host__ __device__ static int total(int nt, int n, int k, int pl, int raw) { return raw_off(nt, n, k, pl) + raw * RAW_STAGE + TAIL; }
-};
+// shared-memory map: [ B planes | staging tile | rank table(s) | run bases | A planes ring | raw ring | barriers, tmem slot ]
+__host__ inline int sk_layout(int nt, StemTcArgs& a, int pl) {
+    auto up = [](int x, int q) { return (x + q - 1) / q * q; };
+    const int nkb = a.K / TC_BK;
+    const int nruns = (TC_BM * a.N) >> a.run_shift;
+    a.off_stg = up(nkb * nt * 128, 1024);
+    a.off_tab = a.off_stg + up(TC_BM * a.N * 8, 1024);
+    a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
+    a.off_apl = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
+    a.off_raw = a.off_apl + pl * SK_APL_STAGE;
+    int raw = (SK_BUDGET - (SK_NBARS * 8 + 16) - a.off_raw) / SK_RAW_STAGE;
+    if (raw > SK_RAW_MAX) raw = SK_RAW_MAX;
+    a.pl_stages = pl;
+    a.raw_stages = raw;
+    a.off_bar = a.off_raw + (raw > 0 ? raw : 0) * SK_RAW_STAGE;
+    return raw;
+}
 
-template <int NT>   // UMMA N (16, 32, 64)
+// small operand: 4 consecutive k of one column -> rows `row` (re) and `NT + row` (im) of the hi and lo planes
+__device__ __forceinline__ void split_store_b(uint8_t* kb_base, int plane_bytes, int nt, int row, int kc, const float2 v[4], int conj) {
+    float rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float re = v[i].x, im = conj ? -v[i].y : v[i].y;
+        rh[i] = tf32_hi(re); rl[i] = re - rh[i];
+        ih[i] = tf32_hi(im); il[i] = im - ih[i];
+    }
+    const int r2 = nt + row;
+    const int off_re = (row >> 3) * 256 + kc * 128 + (row & 7) * 16;
+    const int off_im = (r2 >> 3) * 256 + kc * 128 + (r2 & 7) * 16;
+    *reinterpret_cast<float4*>(kb_base + off_re) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+    *reinterpret_cast<float4*>(kb_base + off_im) = make_float4(ih[0], ih[1], ih[2], ih[3]);
+    *reinterpret_cast<float4*>(kb_base + plane_bytes + off_re) = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    *reinterpret_cast<float4*>(kb_base + plane_bytes + off_im) = make_float4(il[0], il[1], il[2], il[3]);
+}
+
+// bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks stay
+// conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
+__device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
+
+template <int NT>   // columns of the small operand per launch, padded (16, 32, 64); UMMA N = 2*NT
 __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p) {
-    using S = SkSmem;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nkb = (uint32_t)p.K / TC_BK;
     const int64_t ntiles = p.M / TC_BM;
-    constexpr int B_PLANE_KB = NT * TC_BK * 4;                       // bytes of one B plane for one k-block
-    const uint32_t b_plane = nkb * B_PLANE_KB;                       // bytes of one B plane (all k)
+    constexpr int B_KB = 2 * NT * TC_BK * 4;                         // bytes of one B plane ([re | im] rows) per k-block
+    const uint32_t b_plane = nkb * B_KB;                             // bytes of one B plane (all k)
 
-    const int SK_RAW = p.raw_stages;
-    const int STG_OFF = (S::bpl_bytes(NT, p.K) + 1023) / 1024 * 1024;
-    const int POS_OFF = STG_OFF + S::stg_bytes(p.N), RUN_OFF = POS_OFF + (TC_BM * p.N * 2 + 15) / 16 * 16;
-    uint16_t* pos16 = reinterpret_cast<uint16_t*>(smem + POS_OFF);
-    int64_t* runbase = reinterpret_cast<int64_t*>(smem + RUN_OFF);
+    const int SK_RAW = p.raw_stages, SK_PL = p.pl_stages;
+    uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem + p.off_tab); // general: swizzled rank of (col, row)
+    uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem + p.off_tab); // additive: swizzled staging byte offset of column c [NT]
+    int32_t* runbase = reinterpret_cast<int32_t*>(smem + p.off_run);
     const int nruns = (TC_BM * p.N) >> p.run_shift;
-    const bool runs_in_smem = nruns <= S::RUNS_MAX;
-    // bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks
-    // stay conflict free) that spreads ranks which differ by a power-of-two stride over all banks (the writes)
-    auto swz = [](uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); };
-    const int SK_PL = p.pl_stages;
-    const int APL_OFF = S::apl_off(NT, p.N, p.K), RAW_OFF = S::raw_off(NT, p.N, p.K, SK_PL);
-    const int BAR_OFF = RAW_OFF + SK_RAW * S::RAW_STAGE;
-    const uint32_t bar0 = smem_u32(smem + BAR_OFF);
+    bool runs_in_smem = nruns <= SK_RUNS_MAX;
+    const uint32_t bar0 = smem_u32(smem + p.off_bar);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (SK_RAW_MAX + s); };
     auto apl_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + s); };
     auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + SK_PL_MAX + s); };
     auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + s); };
     auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 2 + s); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + S::NBARS * 8);
-    constexpr uint32_t TMEM_COLS = (4 * NT) < 32 ? 32 : 4 * NT;      // two sets of [re NT | im NT]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + SK_NBARS * 8);
+    constexpr uint32_t SET_COLS = 4 * NT;                            // F = [A_re.B_re | A_re.B_im], E = [A_im.B_re | A_im.B_im]
+    constexpr uint32_t TMEM_COLS = 2 * SET_COLS;                     // 128 / 256 / 512
 
     if (tid == 0) {
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
@@ -746,7 +771,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    // small operand -> resident planes (all k-blocks): plane q at q*b_plane, k-block kb at kb*B_PLANE_KB
+    // small operand -> resident planes (all k-blocks): plane q at q*b_plane, k-block kb at kb*B_KB
     for (uint32_t u = tid; u < (uint32_t)NT * nkb * 2; u += SK_THREADS) {
         const uint32_t row = u % NT, r = u / NT, kc = r & 1, kb = r >> 1;
         float2 v[4];
@@ -755,18 +780,31 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             const uint32_t k = kb * TC_BK + kc * 4 + i;
             v[i] = (int)row < p.N ? p.B[tabc(p.bn, p.n0 + row) + tabc(p.bk, k)] : make_float2(0.f, 0.f);
         }
-        split_store(smem + kb * B_PLANE_KB, (int)b_plane, (int)row, (int)kc, v, p.conjB);
+        split_store_b(smem + kb * B_KB, (int)b_plane, NT, (int)row, (int)kc, v, p.conjB);
     }
-    // rank table transposed to [col][row]: the 32 lanes of an epilogue warp (consecutive rows) read consecutive entries
-    for (int i = tid; i < TC_BM * p.N; i += SK_THREADS) {
-        const int row = i / p.N, col = i - row * p.N;
-        pos16[col * TC_BM + row] = (uint16_t)swz((uint32_t)p.pos[i]);
+    if (p.additive) {
+        // separable rank on disjoint bits: staging byte offset of (row, col) = rowoff ^ coloff (the swizzle is XOR-linear)
+        const int64_t p0 = p.pos[0];
+        for (int i = tid; i < NT; i += SK_THREADS) tab32[i] = i < p.N ? 8u * sk_swz((uint32_t)(p.pos[i] - p0)) : 0u;
+    } else {
+        // rank table transposed to [col][row]: the 32 lanes of an epilogue warp (consecutive rows) read consecutive entries
+        for (int i = tid; i < TC_BM * p.N; i += SK_THREADS) {
+            const int row = i / p.N, col = i - row * p.N;
+            tab16[col * TC_BM + row] = (uint16_t)sk_swz((uint32_t)p.pos[i]);
+        }
     }
-    if (runs_in_smem)
-        for (int i = tid; i < nruns; i += SK_THREADS) runbase[i] = p.rel[(int64_t)i << p.run_shift];
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
+    {
+        int big = 0;
+        if (runs_in_smem)
+            for (int i = tid; i < nruns; i += SK_THREADS) {
+                const int64_t v = p.rel[(int64_t)i << p.run_shift];
+                if (v < 0 || v >= ((int64_t)1 << 31)) big = 1;
+                runbase[i] = (int32_t)v;
+            }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        if (__syncthreads_or(big)) runs_in_smem = false;             // pattern spans > 2^31 elements: bases from global
+    }
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -775,7 +813,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         // global k-block counter = plane stage), so two latency chains (wait, LDS, split, STS, proxy fence, arrive)
         // run concurrently; a thread owns one row and both 4-k halves of its k-block. ----
         const int group = warp >> 2, prow = tid & 127;
-        const int raw_row = RAW_OFF + prow * 8;
+        const int raw_row = p.off_raw + prow * 8;
         int64_t my_tiles = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) my_tiles++;
         const uint64_t total_kb = (uint64_t)my_tiles * nkb;
@@ -785,14 +823,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g / (uint64_t)SK_PL) & 1);
             mbar_wait(raw_full(rs), rphase);
             float2 v0[4], v1[4];
-            const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_row;
+            const uint8_t* raw = smem + rs * SK_RAW_STAGE + raw_row;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
                 v1[i] = *reinterpret_cast<const float2*>(raw + (4 + i) * TC_BM * 8);
             }
             mbar_wait(apl_empty(ps), pphase ^ 1);
-            uint8_t* pl = smem + APL_OFF + ps * S::APL_STAGE;
+            uint8_t* pl = smem + p.off_apl + ps * SK_APL_STAGE;
             split_store(pl, TC_BM * TC_BK * 4, prow, 0, v0, p.conjA);
             split_store(pl, TC_BM * TC_BK * 4, prow, 1, v1, p.conjA);
             fence_proxy_async_smem();
@@ -800,91 +838,143 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
         }
     } else if (warp < 16) {
-        // ---- epilogue warps: TMEM -> staging (rank order) -> C (ascending addresses) ----
+        // ---- epilogue warps: TMEM -> combine -> staging (rank order) -> C (ascending addresses) ----
         const int q = warp & 3, half = (warp - 8) >> 2;
         const int etid = tid - SK_WORKERS;                         // 0..255
         const uint32_t row = q * 32 + lane;
-        float2* stg = reinterpret_cast<float2*>(smem + STG_OFF);
+        float2* stg = reinterpret_cast<float2*>(smem + p.off_stg);
         const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
         const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+        const bool unit_alpha = ar == 1.f && ai == 0.f;
         const int cnt = TC_BM * p.N;
         constexpr int COLS = NT >= 32 ? NT / 2 : NT;               // columns per warp (NT = 16: warps of half 1 skip the drain)
         const int cbeg = NT >= 32 ? half * COLS : 0;
         const bool drains = NT >= 32 || half == 0;
+        const bool additive = p.additive != 0;
+        // additive: this thread's row contributes a fixed (swizzled) byte offset
+        const uint32_t rowoff = additive ? 8u * sk_swz((uint32_t)p.pos[(int64_t)row * p.N]) : 0u;
+        uint8_t* stg_b = smem + p.off_stg;
+        const int rmask = (1 << p.run_shift) - 1;
+        const int cend = (cbeg + COLS) < p.N ? (cbeg + COLS) : p.N;   // N is a multiple of 16 (eligibility)
+        // write-out: pair j = 2*etid + 512*it; swz is XOR-linear and the two parts use disjoint bits
+        const uint32_t swz_t = sk_swz((uint32_t)etid * 2u);
+        const bool odd = (swz_t & 1u) != 0;                         // pair stored in swapped order (thread constant)
         uint32_t i = 0;
+        int64_t hi_next = blockIdx.x < ntiles ? p.hi[blockIdx.x] : 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
             const uint32_t set = i & 1;
+            const int64_t hi_cur = hi_next;
+            if (t + gridDim.x < ntiles) hi_next = p.hi[t + gridDim.x];   // in flight while this tile drains
             mbar_wait(accfull_bar(set), (i >> 1) & 1);
             tc_fence_after();
             if (drains) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (2u * NT);
-                const uint16_t* prow = pos16 + row;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * SET_COLS;
 #pragma unroll 1
-                for (int c0 = cbeg; c0 < cbeg + COLS; c0 += 16) {
-                    uint32_t re[16], im[16];
-                    tmem_ld16(taddr + c0, re);
-                    tmem_ld16(taddr + NT + c0, im);
-                    tmem_ld_wait();
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                    uint32_t fr[16], fi[16], er[16], ei[16];
+                    tmem_ld16(taddr + c0, fr);
+                    tmem_ld16(taddr + NT + c0, fi);
+                    tmem_ld16(taddr + 2 * NT + c0, er);
+                    tmem_ld16(taddr + 3 * NT + c0, ei);
+                    if (additive) {
+                        uint32_t co[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (c0 + j < p.N) stg[prow[(c0 + j) * TC_BM]] = make_float2(__uint_as_float(re[j]), __uint_as_float(im[j]));
+                        for (int j = 0; j < 16; j += 4) {
+                            const uint4 c4 = *reinterpret_cast<const uint4*>(tab32 + c0 + j);
+                            co[j] = c4.x; co[j + 1] = c4.y; co[j + 2] = c4.z; co[j + 3] = c4.w;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            *reinterpret_cast<float2*>(stg_b + (rowoff ^ co[j])) =
+                                make_float2(__uint_as_float(fr[j]) - __uint_as_float(ei[j]), __uint_as_float(fi[j]) + __uint_as_float(er[j]));
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            stg[tab16[(c0 + j) * TC_BM + row]] =
+                                make_float2(__uint_as_float(fr[j]) - __uint_as_float(ei[j]), __uint_as_float(fi[j]) + __uint_as_float(er[j]));
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: next-next tile may start
             asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile complete (epilogue warps only)
-            float2* base = p.C + p.hi[t];
-            const int rmask = (1 << p.run_shift) - 1;
-#pragma unroll 4
-            for (int j = etid; j < cnt; j += SK_EPI) {
-                float2 v = stg[swz((uint32_t)j)];
-                float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
-                const int run = j >> p.run_shift;
-                float2* dst = base + (runs_in_smem ? runbase[run] : p.rel[(int64_t)run << p.run_shift]) + (j & rmask);
-                if (has_beta) {
-                    float2 old = *dst;
-                    o.x += br * old.x - bi * old.y;
-                    o.y += br * old.y + bi * old.x;
+            float2* base = p.C + hi_cur;
+            if (p.vec2) {
+                constexpr int U = 4;                                 // pairs in flight per thread; cnt is a multiple of 2048
+                for (int j0 = etid * 2; j0 < cnt; j0 += 2 * SK_EPI * U) {
+                    float4 w[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const uint32_t s = swz_t ^ sk_swz((uint32_t)(j0 - etid * 2 + u * 2 * SK_EPI));
+                        w[u] = *reinterpret_cast<const float4*>(stg + (s & ~1u));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int j = j0 + u * 2 * SK_EPI;
+                        float2 v0 = odd ? make_float2(w[u].z, w[u].w) : make_float2(w[u].x, w[u].y);
+                        float2 v1 = odd ? make_float2(w[u].x, w[u].y) : make_float2(w[u].z, w[u].w);
+                        if (!unit_alpha) {
+                            v0 = make_float2(ar * v0.x - ai * v0.y, ar * v0.y + ai * v0.x);
+                            v1 = make_float2(ar * v1.x - ai * v1.y, ar * v1.y + ai * v1.x);
+                        }
+                        const int run = j >> p.run_shift;
+                        const int64_t rb = runs_in_smem ? (int64_t)runbase[run] : p.rel[(int64_t)run << p.run_shift];
+                        float4* dst = reinterpret_cast<float4*>(base + rb + (j & rmask));
+                        if (has_beta) {
+                            const float4 old = *dst;
+                            v0.x += br * old.x - bi * old.y; v0.y += br * old.y + bi * old.x;
+                            v1.x += br * old.z - bi * old.w; v1.y += br * old.w + bi * old.z;
+                        }
+                        *dst = make_float4(v0.x, v0.y, v1.x, v1.y);
+                    }
                 }
-                *dst = o;
+            } else {
+#pragma unroll 4
+                for (int j = etid; j < cnt; j += SK_EPI) {
+                    float2 v = stg[sk_swz((uint32_t)j)];
+                    float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
+                    const int run = j >> p.run_shift;
+                    const int64_t rb = runs_in_smem ? (int64_t)runbase[run] : p.rel[(int64_t)run << p.run_shift];
+                    float2* dst = base + rb + (j & rmask);
+                    if (has_beta) {
+                        float2 old = *dst;
+                        o.x += br * old.x - bi * old.y;
+                        o.y += br * old.y + bi * old.x;
+                    }
+                    *dst = o;
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile free again
         }
     } else if (warp == 16) {
-        // ---- MMA issuer ----
+        // ---- MMA issuer: 6 MMAs of width 2*NT per k-block; descriptors differ only in their 14-bit address field ----
         if (lane == 0) {
-            constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
+            constexpr uint32_t IDESC = make_idesc<2 * NT>(false);
+            constexpr uint64_t AP16 = (TC_BM * TC_BK * 4) >> 4;
+            const uint64_t adesc0 = make_smem_desc(smem_u32(smem + p.off_apl));
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(smem));
+            const uint64_t bl_off = b_plane >> 4;
             int ps = 0;
             uint32_t pphase = 0, i = 0;
-            const uint32_t sb0 = smem_u32(smem);
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
                 const uint32_t set = i & 1;
                 if (i >= 2) { mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1); tc_fence_after(); }
-                const uint32_t d_re = tmem_base + set * (2u * NT), d_im = d_re + NT;
+                const uint32_t d_f = tmem_base + set * SET_COLS, d_e = d_f + 2 * NT;
                 for (uint32_t kb = 0; kb < nkb; kb++) {
                     mbar_wait(apl_full(ps), pphase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + APL_OFF + ps * S::APL_STAGE);
-                    constexpr uint32_t AP = TC_BM * TC_BK * 4;
-                    const uint32_t sb = sb0 + kb * B_PLANE_KB;
-                    const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + AP),
-                                   a_ih = make_smem_desc(sa + 2 * AP), a_il = make_smem_desc(sa + 3 * AP);
-                    const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + b_plane),
-                                   b_ih = make_smem_desc(sb + 2 * b_plane), b_il = make_smem_desc(sb + 3 * b_plane);
+                    const uint64_t a_rh = adesc0 + (uint64_t)(ps * (SK_APL_STAGE >> 4));
+                    const uint64_t b_h = bdesc0 + (uint64_t)(kb * (B_KB >> 4)), b_l = b_h + bl_off;
                     const uint32_t acc = kb > 0 ? 1u : 0u;
-                    umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
-                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_im, a_rh, b_il, IDESC, acc);
-                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                    umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
-                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_tf32(d_f, a_rh, b_l, IDESC, acc);
+                    umma_tf32(d_f, a_rh + AP16, b_h, IDESC, 1u);
+                    umma_tf32(d_f, a_rh, b_h, IDESC, 1u);
+                    umma_tf32(d_e, a_rh + 2 * AP16, b_l, IDESC, acc);
+                    umma_tf32(d_e, a_rh + 3 * AP16, b_h, IDESC, 1u);
+                    umma_tf32(d_e, a_rh + 2 * AP16, b_h, IDESC, 1u);
                     umma_commit(apl_empty(ps));
                     if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
                 }
@@ -900,10 +990,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             const float2* src = p.A + t * TC_BM;
             for (uint32_t kb = 0; kb < nkb; kb++) {
                 mbar_wait(raw_empty(rs), rphase ^ 1);
-                if (lane == 0) mbar_expect_tx(raw_full(rs), S::RAW_STAGE);
+                if (lane == 0) mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
                 __syncwarp();
                 if (lane < 8) {
-                    const uint32_t dst = smem_u32(smem + RAW_OFF + rs * S::RAW_STAGE + lane * TC_BM * 8);
+                    const uint32_t dst = smem_u32(smem + p.off_raw + rs * SK_RAW_STAGE + lane * TC_BM * 8);
                     bulk_g2s(dst, src + (int64_t)(kb * TC_BK + lane) * p.lda, TC_BM * 8, raw_full(rs));
                 }
                 if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
@@ -922,11 +1012,10 @@ template <int NT>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     // four plane stages (a worker group refills one while the tensor core reads its other one) if that still leaves
     // >= 5 raw stages (40 KB of bulk copies in flight), else two
-    a.pl_stages = SkSmem::raw_stages(NT, a.N, a.K, 4) >= 5 ? 4 : 2;
-    a.raw_stages = SkSmem::raw_stages(NT, a.N, a.K, a.pl_stages);
+    if (sk_layout(NT, a, 4) < 5) sk_layout(NT, a, 2);
     if (a.raw_stages < 3) return -1;
-    const int smem = SkSmem::total(NT, a.N, a.K, a.pl_stages, a.raw_stages);
-    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkSmem::BUDGET));
+    const int smem = a.off_bar + SK_NBARS * 8 + 16;
+    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     c64_tf32x3_stem_kernel<NT><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a);
@@ -934,6 +1023,7 @@ int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
 }
+
 
 // cp.async.bulk needs 16-byte aligned rows: even M, N and leading dimensions, 16-byte aligned bases
 bool tc_acc_ok(const TcArgs& a) {
@@ -1008,10 +1098,12 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
     if ((e.lda % 2) != 0 || ((uintptr_t)e.A % 16) != 0) return -1;
     StemTcArgs a;
     a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
-    a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.n0 = e.n0; a.contig = e.contig; a.conjA = e.conjA; a.conjB = e.conjB;
+    a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.n0 = e.n0; a.conjA = e.conjA; a.conjB = e.conjB;
     a.bn = e.bn; a.bk = e.bk; a.hi = e.hi; a.rel = e.rel; a.pos = e.pos;
     a.run_shift = 0;
     while ((1 << (a.run_shift + 1)) <= e.run) a.run_shift++;
+    a.additive = e.additive;
+    a.vec2 = (e.run >= 2 && e.even && ((uintptr_t)e.C % 16) == 0) ? 1 : 0;
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
     if (e.N <= 16) return launch_stem_tc<16>(ctx, a);

@@ -8,6 +8,7 @@
 // its single consumer reads it as a dense, M-fastest matrix.
 //
 // Pure host code: no CUDA calls here, so the same code backs the dry-run plans that CPU tests inspect.
+#include <cstdlib>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -287,6 +288,21 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
             R = std::min(R, r);
         }
         S.st_run = (int32_t)R;
+        // rank separable in (row, column) on disjoint bits?  (always true for power-of-two extents: the rank is a bit deposit)
+        bool additive = getenv("TNB_STEM_NO_ADDITIVE") == nullptr, even = R >= 2;   // env: test hook for the table path
+        for (int64_t ps = 0; ps < passes && additive; ps++) {
+            const int64_t* pos = S.st_pos.data() + ps * cnt;
+            for (int64_t ml = 0; ml < TM && additive; ml++)
+                for (int64_t n = 0; n < ncol; n++)
+                    if (pos[ml * ncol + n] != pos[ml * ncol] + pos[n] - pos[0] || (pos[ml * ncol] & (pos[n] - pos[0])) != 0) { additive = false; break; }
+        }
+        for (int64_t v : cb.hi) if (v & 1) even = false;
+        for (int64_t j = 0; j < cnt * passes && even; j += R) if (S.st_rel[(size_t)j] & 1) even = false;
+        S.st_additive = additive; S.st_even = even;
+        if (getenv("TNB_DEBUG_STEM"))
+            fprintf(stderr, "[stem] M=%lld N=%lld K=%lld big=%lld small=%lld tc=%d swap=%d TM=%lld ncol=%lld passes=%lld run=%lld additive=%d even=%d contig=%d\n",
+                    (long long)S.M, (long long)S.N, (long long)S.K, (long long)Mb, (long long)Ns, (int)!simt, sw, (long long)TM,
+                    (long long)ncol, (long long)passes, (long long)R, (int)additive, (int)even, (int)contig);
         S.st_npass = (int32_t)passes; S.st_ncol = (int32_t)ncol;
         S.st_hi = cb.hi;
         S.st_ok = true; S.st_swap = sw != 0; S.st_tm = (int32_t)TM; S.st_contig = contig;

@@ -74,6 +74,7 @@ struct StepSpec {
     // streaming "stem" kernel (huge dense operand x tiny operand): tile-invariant sorted output pattern
     bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
     int32_t st_npass = 1, st_ncol = 0;   // passes over the small operand's columns, columns per pass
+    bool st_additive = false, st_even = false;   // see StemArgs
     int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
@@ -152,6 +153,8 @@ struct StemArgs {
     int32_t N, K, TM, contig, conjA, conjB;
     int32_t n0;               // first column of the small operand handled by this launch (multi-pass)
     int32_t run;              // contiguous run length of the sorted pattern (power of two): rel[j] = rel[j & ~(run-1)] + (j & (run-1))
+    int32_t additive;         // pos[ml*N + n] == pos[ml*N] | (pos[n] - pos[0]), disjoint bits (rank separable in row and column)
+    int32_t even;             // every tile base (hi) and every run base (rel[j*run]) is even: 16-byte aligned pairs
     TabRef bn, bk;
     const int64_t* hi;        // [M/TM] tile base offsets in C
     const int64_t* rel;       // [TM*N] ascending offsets inside a tile

@@ -180,7 +180,8 @@ def test_stem_tc_kernel(ctx, N, K):
     ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"])
     hi = np.complex128
     ref = np.tensordot(a.astype(hi), b.astype(hi), axes=([17], [1]))          # m0..m16, n
-    for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8]]:
+    # last layout: the fastest output mode is neither in the tile nor in the small operand -> runs of one element
+    for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8], big[8:] + ["n"] + big[:8]]:
         c = tb.binary_einsum(ta, tb_, out=out)
         assert ctx.last_kernel == "stem_tc", ctx.last_kernel
         r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
@@ -190,3 +191,22 @@ def test_stem_tc_kernel(ctx, N, K):
     assert ctx.last_kernel == "stem_tc"
     r = np.transpose(np.tensordot(a.astype(hi), np.conj(b).astype(hi), axes=([17], [1])), [17] + list(range(17)))
     assert np.abs(c.parent - r).max() / np.abs(r).max() < 1e-5
+
+
+def test_stem_tc_rank_table_path(ctx, monkeypatch):
+    """the general (non-separable rank) epilogue of the stem kernel: forced through TNB_STEM_NO_ADDITIVE."""
+    import tenet_jl_b200 as tb
+    monkeypatch.setenv("TNB_STEM_NO_ADDITIVE", "1")
+    rng = np.random.default_rng(5)
+    a = crand(rng, (2,) * 17 + (32,))
+    b = crand(rng, (32, 32))
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"])
+    hi = np.complex128
+    ref = np.tensordot(a.astype(hi), b.astype(hi), axes=([17], [1]))
+    for out in [big[:3] + ["n"] + big[3:], big[9:] + ["n"] + big[:9]]:
+        c = tb.binary_einsum(ta, tb_, out=out)
+        assert ctx.last_kernel == "stem_tc", ctx.last_kernel
+        r = np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        err = np.abs(c.parent - r).max() / np.abs(r).max()
+        assert err < 1e-5, err
