@@ -41,7 +41,7 @@ WORKLOADS = {
 }
 
 
-def build_workload(tb, name):
+def build_workload(tb, name, path_file=""):
     """-> (TensorNetwork, ContractionPath, dtype)"""
     from tools.make_paths import network  # noqa
     if name == "peps6x6_d4_boundary":
@@ -49,7 +49,7 @@ def build_workload(tb, name):
         return tn, tb.workloads.peps_boundary_path(6, 6)
     if name in ("sycamore53_m14", "sycamore53_m14_greedy", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
         tn = network(name)
-        fn = os.path.join(ROOT, "bench_paths", name + ".json")
+        fn = path_file or os.path.join(ROOT, "bench_paths", name + ".json")
         if not os.path.exists(fn):
             raise SystemExit(f"{fn} missing: run `python tools/make_paths.py {name}`")
         path = tb.pathfinder.load_path(tn.inds("all"), fn)
@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--c64-mode", default="auto", choices=["auto", "simt", "tf32x3", "tf32x3_fast"])
     ap.add_argument("--dump-steps", default="")
+    ap.add_argument("--path-file", default="", help="candidate path JSON to use instead of bench_paths/<workload>.json")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -157,7 +158,7 @@ def main():
     g.build()
     import tenet_jl_b200 as tb
 
-    tn, path = build_workload(tb, a.workload)
+    tn, path = build_workload(tb, a.workload, a.path_file)
     dtype = tb.tensor._promote_dtype(*[t.dtype for t in tn.tensors])
     cplx = dtype.kind == "c"
     flops_unit = 8.0 if cplx else 2.0

@@ -89,7 +89,7 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
         }
         if (S.st_ok && S.st_tc && dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT)) {
             S.kernel = TNB_KERNEL_STEM_TC;
-            return 0;
+            return tnb_stem_tc_ws_elems(S.st_ncol, S.K, S.st_npass);
         }
         const bool tc_ok = dtype == TNB_C64 && (!ctx || ctx->c64_mode != TNB_C64_SIMT) &&
                            (double)S.M * (double)S.N * (double)S.K >= (double)(1ll << 18);
@@ -150,7 +150,7 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         for (int ps = 0; ps < S.st_npass; ps++) {
             t.N = S.st_ncol; t.n0 = ps * S.st_ncol;
             t.rel = dev_blob + S.st_rel_pos + ps * cnt; t.pos = dev_blob + S.st_pos_pos + ps * cnt;
-            int rc = tnb_launch_c64_stem_tc(ctx, t);
+            int rc = tnb_launch_c64_stem_tc(ctx, t, ws, S.st_npass);
             if (rc == -1 && ps == 0)
                 return tnb_launch_einsum_generic(ctx, dtype, a);  // misaligned big operand: exact-FP32 generic kernel
             if (rc) return rc;

@@ -676,7 +676,8 @@ constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as 
 constexpr int SK_RUNS_MAX = 1024;               // run bases kept in shared memory (int32)
 constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
 constexpr int SK_APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
-constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4;
+constexpr int SK_BST = 4;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
+constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + 2 * SK_BST;
 constexpr int SK_BUDGET = 227 * 1024;
 
 struct StemTcArgs {
@@ -691,6 +692,7 @@ struct StemTcArgs {
     int32_t additive;         // pos[row*N + col] == pos[row*N] + pos[col] - pos[0]
     int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
     int32_t off_stg, off_tab, off_run, off_apl, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
+    const uint8_t* bplanes;   // streamed-B mode: pre-split planes of this pass in global memory, [kb][hi|lo][2*NT rows x 32 B]
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
     const int64_t* rel;       // [128*N]
@@ -703,7 +705,7 @@ __host__ inline int sk_layout(int nt, StemTcArgs& a, int pl) {
     auto up = [](int x, int q) { return (x + q - 1) / q * q; };
     const int nkb = a.K / TC_BK;
     const int nruns = (TC_BM * a.N) >> a.run_shift;
-    a.off_stg = up(nkb * nt * 128, 1024);
+    a.off_stg = up((a.bplanes ? SK_BST : nkb) * nt * 128, 1024);
     a.off_tab = a.off_stg + up(TC_BM * a.N * 8, 1024);
     a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
     a.off_apl = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
@@ -738,7 +740,10 @@ __device__ __forceinline__ void split_store_b(uint8_t* kb_base, int plane_bytes,
 // conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
 __device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
 
-template <int NT>   // columns of the small operand per launch, padded (16, 32, 64); UMMA N = 2*NT
+// BSTREAM: the small operand's planes do not fit in shared memory (N*K*16 > 64 KB): a tiny pre-pass
+// (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and the copy warp streams one
+// 2*B_KB stage per k-block (one bulk copy, L2-resident source) next to the A rows.
+template <int NT, bool BSTREAM>   // NT: columns of the small operand per launch, padded (16, 32, 64); UMMA N = 2*NT
 __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -760,6 +765,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     auto apl_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + SK_PL_MAX + s); };
     auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + s); };
     auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 2 + s); };
+    auto b_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + s); };
+    auto b_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + SK_BST + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + SK_NBARS * 8);
     constexpr uint32_t SET_COLS = 4 * NT;                            // F = [A_re.B_re | A_re.B_im], E = [A_im.B_re | A_im.B_im]
     constexpr uint32_t TMEM_COLS = 2 * SET_COLS;                     // 128 / 256 / 512
@@ -768,11 +775,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
         for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32); }
+        for (int s = 0; s < SK_BST; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     // small operand -> resident planes (all k-blocks): plane q at q*b_plane, k-block kb at kb*B_KB
-    for (uint32_t u = tid; u < (uint32_t)NT * nkb * 2; u += SK_THREADS) {
+    for (uint32_t u = tid; !BSTREAM && u < (uint32_t)NT * nkb * 2; u += SK_THREADS) {
         const uint32_t row = u % NT, r = u / NT, kc = r & 1, kb = r >> 1;
         float2 v[4];
 #pragma unroll
@@ -956,9 +964,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             constexpr uint64_t AP16 = (TC_BM * TC_BK * 4) >> 4;
             const uint64_t adesc0 = make_smem_desc(smem_u32(smem + p.off_apl));
             const uint64_t bdesc0 = make_smem_desc(smem_u32(smem));
-            const uint64_t bl_off = b_plane >> 4;
-            int ps = 0;
-            uint32_t pphase = 0, i = 0;
+            const uint64_t bl_off = BSTREAM ? (uint64_t)(B_KB >> 4) : (uint64_t)(b_plane >> 4);
+            int ps = 0, bs = 0;
+            uint32_t pphase = 0, bphase = 0, i = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
                 const uint32_t set = i & 1;
                 if (i >= 2) { mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1); tc_fence_after(); }
@@ -967,7 +975,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                     mbar_wait(apl_full(ps), pphase);
                     tc_fence_after();
                     const uint64_t a_rh = adesc0 + (uint64_t)(ps * (SK_APL_STAGE >> 4));
-                    const uint64_t b_h = bdesc0 + (uint64_t)(kb * (B_KB >> 4)), b_l = b_h + bl_off;
+                    if (BSTREAM) { mbar_wait(b_full(bs), bphase); tc_fence_after(); }
+                    const uint64_t b_h = bdesc0 + (uint64_t)((BSTREAM ? 2u * bs : kb) * (B_KB >> 4)), b_l = b_h + bl_off;
                     const uint32_t acc = kb > 0 ? 1u : 0u;
                     umma_tf32(d_f, a_rh, b_l, IDESC, acc);
                     umma_tf32(d_f, a_rh + AP16, b_h, IDESC, 1u);
@@ -977,6 +986,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                     umma_tf32(d_e, a_rh + 2 * AP16, b_h, IDESC, 1u);
                     umma_commit(apl_empty(ps));
                     if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
+                    if (BSTREAM) {
+                        umma_commit(b_empty(bs));
+                        if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                    }
                 }
                 umma_commit(accfull_bar(set));
             }
@@ -984,11 +997,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         __syncwarp();
     } else {
         // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile ----
-        int rs = 0;
-        uint32_t rphase = 0;
+        int rs = 0, bs = 0;
+        uint32_t rphase = 0, bphase = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const float2* src = p.A + t * TC_BM;
             for (uint32_t kb = 0; kb < nkb; kb++) {
+                if (BSTREAM) {
+                    mbar_wait(b_empty(bs), bphase ^ 1);
+                    if (lane == 8) {
+                        mbar_expect_tx(b_full(bs), 2 * B_KB);
+                        bulk_g2s(smem_u32(smem + bs * 2 * B_KB), p.bplanes + (size_t)kb * 2 * B_KB, 2 * B_KB, b_full(bs));
+                    }
+                    if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                }
                 mbar_wait(raw_empty(rs), rphase ^ 1);
                 if (lane == 0) mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
                 __syncwarp();
@@ -1008,22 +1029,39 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     }
 }
 
+// pre-pass of the streamed-B mode: split the small operand once into global memory, [pass][kb][hi|lo][2*NT rows x 32 B]
 template <int NT>
+__global__ void stem_bsplit_kernel(const float2* __restrict__ B, TabRef bn, TabRef bk, int N, int conjB, uint8_t* __restrict__ out) {
+    constexpr int B_KB = 2 * NT * TC_BK * 4;
+    const uint32_t kb = blockIdx.x, pass = blockIdx.y, nkb = gridDim.x;
+    uint8_t* dst = out + ((size_t)pass * nkb + kb) * 2 * B_KB;
+    for (uint32_t u = threadIdx.x; u < (uint32_t)NT * 2; u += blockDim.x) {
+        const uint32_t row = u % NT, kc = u / NT;
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t k = kb * TC_BK + kc * 4 + i;
+            v[i] = (int)row < N ? B[tabc(bn, pass * NT + row) + tabc(bk, k)] : make_float2(0.f, 0.f);
+        }
+        split_store_b(dst, B_KB, NT, (int)row, (int)kc, v, conjB);
+    }
+}
+
+template <int NT, bool BSTREAM>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     // four plane stages (a worker group refills one while the tensor core reads its other one) if that still leaves
     // >= 5 raw stages (40 KB of bulk copies in flight), else two
     if (sk_layout(NT, a, 4) < 5) sk_layout(NT, a, 2);
     if (a.raw_stages < 3) return -1;
     const int smem = a.off_bar + SK_NBARS * 8 + 16;
-    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
+    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    c64_tf32x3_stem_kernel<NT><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a);
+    c64_tf32x3_stem_kernel<NT, BSTREAM><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
 }
-
 
 // cp.async.bulk needs 16-byte aligned rows: even M, N and leading dimensions, 16-byte aligned bases
 bool tc_acc_ok(const TcArgs& a) {
@@ -1088,15 +1126,25 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
 }
 
 // Plan-time eligibility of the persistent tensor-core stem kernel (sizes only; density is checked by the planner).
+// Small operand resident in shared memory (N*K*16 <= 64 KB), or streamed per k-block from a pre-split copy (64 columns
+// per pass, K <= 128: the regime where the tile GEMM kernel's per-tile prologue/epilogue is not amortised).
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
-    return Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K <= 128 &&
-           K % TC_BK == 0 && Nsmall * K * 16 <= 64 * 1024;
+    if (!(Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K % TC_BK == 0)) return false;
+    if (K <= 128 && Nsmall * K * 16 <= 64 * 1024) return true;
+    return Nsmall == 64 && K <= 128;
+}
+// workspace (in complex64 elements) the streamed-B mode needs for `npass` passes of `Nsmall` columns; 0 = resident mode
+int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass) {
+    if (Nsmall * K * 16 <= 64 * 1024) return 0;
+    return npass * (K / TC_BK) * (128 * Nsmall) / 8;
 }
 
-// returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back)
-int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
+// returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back).
+// ws: streamed-B workspace for ALL passes (pass e.n0 / e.N uses its slice); the pre-split runs with the first pass.
+int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass) {
     if ((e.lda % 2) != 0 || ((uintptr_t)e.A % 16) != 0) return -1;
     StemTcArgs a;
+    memset(&a, 0, sizeof a);
     a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
     a.M = e.M; a.lda = e.lda; a.N = e.N; a.K = e.K; a.n0 = e.n0; a.conjA = e.conjA; a.conjB = e.conjB;
     a.bn = e.bn; a.bk = e.bk; a.hi = e.hi; a.rel = e.rel; a.pos = e.pos;
@@ -1106,7 +1154,20 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e) {
     a.vec2 = (e.run >= 2 && e.even && ((uintptr_t)e.C % 16) == 0) ? 1 : 0;
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
-    if (e.N <= 16) return launch_stem_tc<16>(ctx, a);
-    if (e.N <= 32) return launch_stem_tc<32>(ctx, a);
-    return launch_stem_tc<64>(ctx, a);
+    const bool stream = tnb_stem_tc_ws_elems(e.N, e.K, 1) > 0;
+    if (stream) {
+        if (!ws || e.N != 64) return -1;
+        const int nkb = e.K / TC_BK;
+        const size_t pass_bytes = (size_t)nkb * 128 * 64;
+        if (e.n0 == 0) {
+            stem_bsplit_kernel<64><<<dim3(nkb, npass), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
+            ctx->launches++;
+            TNB_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+        a.bplanes = (const uint8_t*)ws + (size_t)(e.n0 / 64) * pass_bytes;
+        return launch_stem_tc<64, true>(ctx, a);
+    }
+    if (e.N <= 16) return launch_stem_tc<16, false>(ctx, a);
+    if (e.N <= 32) return launch_stem_tc<32, false>(ctx, a);
+    return launch_stem_tc<64, false>(ctx, a);
 }

@@ -163,7 +163,8 @@ struct StemArgs {
 };
 int tnb_launch_stem(tnb_ctx* ctx, int dtype, const StemArgs& a);
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K);
-int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e);
+int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass);
+int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass);
 
 // kernels_c128_dmma.cu
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);

@@ -20,7 +20,7 @@ from .pathfinder import ContractionPath, _Net, _greedy_once, _logaddexp2, path_c
 
 # "time" objective: a pairwise step costs max(MACs, BYTE_WEIGHT * elements moved) — on the B200 engine a complex64
 # element moved through HBM (8 B at ~3.3 TB/s achieved) costs as much time as ~73 complex MACs (8 flop at ~240 TFLOP/s).
-BYTE_WEIGHT_LOG2 = math.log2(73.0)
+BYTE_WEIGHT_LOG2 = math.log2(float(__import__('os').environ.get('TNB_BYTE_WEIGHT', '73')))
 
 
 def _step_cost(net, la_mask, lb_mask, lc_mask, minimize):

@@ -168,7 +168,7 @@ def test_stem_stream_kernel(ctx, dt, tol):
     assert np.abs(c.parent - r).max() / np.abs(r).max() < tol * 4
 
 
-@pytest.mark.parametrize("N,K", [(16, 16), (32, 128), (64, 64), (48, 8), (64, 16), (128, 64), (256, 16)])
+@pytest.mark.parametrize("N,K", [(16, 16), (32, 128), (64, 64), (48, 8), (64, 16), (128, 64), (256, 16), (64, 128), (128, 128), (256, 96)])
 def test_stem_tc_kernel(ctx, N, K):
     """persistent tcgen05 stem kernel: huge x small, several consumer layouts, both orientations."""
     import tenet_jl_b200 as tb
