@@ -76,11 +76,17 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
     S.kchunk = S.K;
     S.tc_nt = 0;
     S.tc_swap = false;
+    S.kred = false;
     const bool force_generic = ctx && ctx->force_generic;
     if (!force_generic) {
         int thin = tnb_choose_thin(ctx, S.M, S.N, S.K, S.L, &kchunk, &ws_elems);
         if (thin > 0) {
             S.kernel = TNB_KERNEL_STREAM; S.splitk = thin; S.kchunk = kchunk;
+            return ws_elems;
+        }
+        int kred = tnb_choose_kred(ctx, dtype, S.M, S.N, S.K, S.L, S.a_mmajor, S.b_nmajor, &kchunk, &ws_elems);
+        if (kred > 0) {
+            S.kernel = TNB_KERNEL_STREAM; S.kred = true; S.splitk = kred; S.kchunk = kchunk;
             return ws_elems;
         }
         if (S.st_ok && !S.st_tc && (dtype == TNB_C64 || dtype == TNB_C128)) {
@@ -190,7 +196,10 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
     }
     if (S.kernel == TNB_KERNEL_STREAM && ws) {
         a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;
-        int rc = tnb_launch_einsum_thin(ctx, dtype, a);
+        int rc = S.kred ? tnb_launch_einsum_kred(ctx, dtype, a) : tnb_launch_einsum_thin(ctx, dtype, a);
+        if (rc == -1) {   // misaligned operands: same split through the generic kernel
+            rc = tnb_launch_einsum_generic(ctx, dtype, a);
+        }
         if (rc) return rc;
         return tnb_launch_splitk_reduce(ctx, dtype, a);
     }

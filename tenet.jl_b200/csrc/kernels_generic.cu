@@ -349,6 +349,109 @@ __global__ void __launch_bounds__(THIN_THREADS) einsum_thin_kernel(const EinsumA
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// "k-reduction" kernel: small M x N (M*N <= 512), K huge, L == 1, complex, both operands dense [K][M] / [K][N]
+// (free index fastest — what the planner's layouts give every intermediate).  HBM-bound (AI = MN/(M+N) <= ~12 flop/B):
+// a CTA streams a contiguous K chunk tile by tile (KS k's = one contiguous block of KS*M resp. KS*N elements, fetched
+// with 16-byte cp.async into a two-stage ring), threads are (k-slice, 2 x 4 micro-tile of C): per k a thread reads
+// 2 A and 4 B elements (three LDS.128) for 8 complex MACs.  Partials of the k-slices are summed in shared memory in a
+// fixed order, one partial per CTA goes to the split-K workspace, the deterministic reducer finishes.
+// Algorithmic bytes per launch: sizeof(T) * (M + N) * K.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KRED_THREADS = 256;
+
+struct KredArgs {
+    const void* A; const void* B; void* ws;
+    int64_t K, kchunk;
+    int32_t M, N, KS, kslices, mt, nt, conjA, conjB;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+template <typename E>   // float2 / double2
+__global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArgs p) {
+    extern __shared__ __align__(16) unsigned char kred_smem[];
+    constexpr int VEC = 16 / (int)sizeof(E);                       // elements per 16-byte copy
+    const int M = p.M, N = p.N, KS = p.KS;
+    const int tileA = KS * M, tileB = KS * N, stage_elems = tileA + tileB;
+    E* sm = reinterpret_cast<E*>(kred_smem);
+    const E* __restrict__ A = (const E*)p.A;
+    const E* __restrict__ B = (const E*)p.B;
+    const int64_t k_begin = (int64_t)blockIdx.x * p.kchunk;
+    const int64_t k_end = (k_begin + p.kchunk) < p.K ? (k_begin + p.kchunk) : p.K;
+    const int ntile = k_begin < k_end ? (int)((k_end - k_begin + KS - 1) / KS) : 0;
+    const int tid = threadIdx.x;
+
+    auto load = [&](int stage, int t) {
+        const int64_t k0 = k_begin + (int64_t)t * KS;
+        const int64_t kv = (k_end - k0) < KS ? (k_end - k0) : KS;  // valid k's in this tile
+        E* dA = sm + stage * stage_elems;
+        E* dB = dA + tileA;
+        const E* gA = A + k0 * M;
+        const E* gB = B + k0 * N;
+        for (int i = tid * VEC; i < tileA; i += KRED_THREADS * VEC) cp_async16_zfill(dA + i, gA + i, i < kv * M);
+        for (int i = tid * VEC; i < tileB; i += KRED_THREADS * VEC) cp_async16_zfill(dB + i, gB + i, i < kv * N);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int per = p.mt * p.nt;
+    const bool active = tid < p.kslices * per;
+    const int ks = tid / per, r = tid - ks * per;
+    const int m0 = (r / p.nt) * 2, n0 = (r % p.nt) * 4;
+    E acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = ezero((E*)0);
+
+    if (ntile > 0) load(0, 0);
+    for (int t = 0; t < ntile; t++) {
+        if (t + 1 < ntile) { load((t + 1) & 1, t + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (active) {
+            const E* sA = sm + (t & 1) * stage_elems;
+            const E* sB = sA + tileA;
+#pragma unroll 4
+            for (int kk = ks; kk < KS; kk += p.kslices) {
+                E a[2], b[4];
+                a[0] = sA[kk * M + m0]; a[1] = sA[kk * M + m0 + 1];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = sB[kk * N + n0 + j];
+                if (p.conjA) { a[0] = econj(a[0]); a[1] = econj(a[1]); }
+                if (p.conjB) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) b[j] = econj(b[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) emac(acc[i][j], a[i], b[j]);
+            }
+        }
+        __syncthreads();
+    }
+    // k-slice partials -> shared (reusing the ring), summed in slice order
+    E* red = sm;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) red[(size_t)ks * M * N + (n0 + j) * M + m0 + i] = acc[i][j];
+    }
+    __syncthreads();
+    for (int o = tid; o < M * N; o += KRED_THREADS) {
+        E s = ezero((E*)0);
+        for (int q = 0; q < p.kslices; q++) s = eadd(s, red[(size_t)q * M * N + o]);
+        ((E*)p.ws)[(uint64_t)blockIdx.x * M * N + o] = s;           // ws[(cta*N + n)*M + m]
+    }
+}
+
 }  // namespace
 
 // thin path: returns number of CTAs (= splitk) or 0 if not applicable
@@ -447,4 +550,49 @@ int tnb_launch_splitk_reduce(tnb_ctx* ctx, int dtype, const EinsumArgs& args) {
         case TNB_F32: return launch_reduce<float, false>(ctx, args);
     }
     return tnb_set_error(ctx, TNB_EUNSUPPORTED, "unsupported dtype %d", dtype);
+}
+
+// k-reduction path (dense operands, small M x N, huge K): returns the number of CTAs (= splitk), 0 if not applicable
+int tnb_choose_kred(const tnb_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor,
+                    int64_t* kchunk, int64_t* ws_elems) {
+    if (!tnb_dtype_complex(dtype) || L != 1 || !a_mmajor || !b_nmajor || K < 16384) return 0;
+    if (M < 2 || N < 4 || (M % 2) || (N % 4) || M * N > 512 || M > 64 || N > 128) return 0;
+    const int64_t sms = ctx ? ctx->sm_count : 148;
+    int64_t ctas = sms * 4;
+    const int64_t per = 128;                                   // multiple of every KS
+    int64_t kc = (K + ctas - 1) / ctas;
+    kc = (kc + per - 1) / per * per;
+    ctas = (K + kc - 1) / kc;
+    *kchunk = kc;
+    *ws_elems = ctas * M * N;
+    return (int)ctas;
+}
+
+int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
+    const size_t esz = tnb_dtype_size(dtype);
+    if (((uintptr_t)a.A % 16) || ((uintptr_t)a.B % 16)) return -1;
+    KredArgs k;
+    k.A = a.A; k.B = a.B; k.ws = a.ws; k.K = a.K; k.kchunk = a.kchunk;
+    k.M = (int32_t)a.M; k.N = (int32_t)a.N; k.conjA = a.conjA; k.conjB = a.conjB;
+    k.mt = k.M / 2; k.nt = k.N / 4;
+    int ks = 1;
+    while (ks * 2 * k.mt * k.nt <= KRED_THREADS) ks *= 2;
+    k.kslices = ks;
+    int KS = 128;                                              // stage <= 24 KB
+    while (KS > 16 && (size_t)KS * (k.M + k.N) * esz > 24 * 1024) KS /= 2;
+    if (KS < ks) KS = ks;
+    k.KS = KS;
+    size_t smem = 2 * (size_t)KS * (k.M + k.N) * esz;
+    const size_t red = (size_t)ks * k.M * k.N * esz;
+    if (red > smem) smem = red;
+    if (dtype == TNB_C64) {
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_kred_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        einsum_kred_kernel<float2><<<(unsigned)a.splitk, KRED_THREADS, smem, ctx->stream>>>(k);
+    } else {
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_kred_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        einsum_kred_kernel<double2><<<(unsigned)a.splitk, KRED_THREADS, smem, ctx->stream>>>(k);
+    }
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
 }

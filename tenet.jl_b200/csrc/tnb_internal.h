@@ -78,6 +78,7 @@ struct StepSpec {
     int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
+    bool kred = false;       // STREAM kernel variant: dense k-reduction kernel (small M x N, huge K)
     int32_t tc_nt = 0;       // tcgen05 kernel: N tile (256/128), 0 = not used
     bool tc_swap = false;    // tcgen05 kernel: operands swapped (C^T = B A^T)
 };
@@ -139,6 +140,9 @@ int tnb_choose_splitk(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64
 
 int tnb_choose_thin(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);
 int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
+int tnb_choose_kred(const tnb_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor,
+                    int64_t* kchunk, int64_t* ws_elems);
+int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& args);   // -1: operands not 16-byte aligned
 // kernels_c64_tc.cu
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);

@@ -87,6 +87,34 @@ def test_thin_reduction(ctx, dt, tol, M, N):
         assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
 
 
+@pytest.mark.parametrize("dt,tol", [(np.complex64, 1e-5), (np.complex128, 1e-13)])
+@pytest.mark.parametrize("M,N", [(8, 32), (2, 4), (16, 32), (4, 128), (6, 12)])
+def test_k_reduction_kernel(ctx, dt, tol, M, N):
+    """small M x N, huge K, dense operands with the free index fastest (the environment-closing steps of a sliced
+    path; storage is column-major like Julia): HBM-bound k-reduction kernel; ragged K, conj flags, high-rank groups."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(M * 7 + N)
+    hi = np.complex128
+    for K in (1 << 18, 300007):
+        a, b = crand(rng, (M, K), dt), crand(rng, (N, K), dt)
+        c = tb.binary_einsum(tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("n", "k")))
+        assert ctx.last_kernel == "stream", ctx.last_kernel
+        ref = a.astype(hi) @ b.astype(hi).T
+        assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
+    c = tb.binary_einsum(tb.Tensor(a, ("m", "k")).conj(), tb.Tensor(b, ("n", "k")), out=("n", "m"))
+    assert ctx.last_kernel == "stream"
+    ref = (np.conj(a).astype(hi) @ b.astype(hi).T).T
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
+    if M == 8:
+        a4 = a[:, : 1 << 18].reshape(2, 2, 2, 64, 64, 64)
+        b4 = b[:, : 1 << 18].reshape(4, 8, 64, 64, 64)
+        c = tb.binary_einsum(tb.Tensor(a4, ("m0", "m1", "m2", "k0", "k1", "k2")), tb.Tensor(b4, ("n0", "n1", "k0", "k1", "k2")))
+        assert ctx.last_kernel == "stream"
+        ref = np.einsum("xyzabc,uvabc->xyzuv", a4.astype(hi), b4.astype(hi))
+        got = np.transpose(np.asarray(c.parent), [list(c.inds).index(i) for i in ("m0", "m1", "m2", "n0", "n1")])
+        assert np.abs(got - ref).max() / np.abs(ref).max() < tol * 10
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 8), (33, 47, 5), (200, 130, 77), (64, 512, 256), (1000, 8, 300), (256, 256, 4096)])
 def test_c128_dmma_matches_oracle(ctx, M, N, K):
     """FP64 tensor-core kernel: ragged edges, operand swap (N > M), split-K, against c128 numpy (1e-12)."""
