@@ -19,6 +19,7 @@
 //   c64_tf32x3_stem_kernel<NT> persistent HBM-bound kernel for huge x small steps (small operand resident as planes,
 //                              sorted-pattern coalesced epilogue overlapped with the next tile)
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "tnb_internal.h"
 
@@ -676,6 +677,8 @@ constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as 
 constexpr int SK_RUNS_MAX = 1024;               // run bases kept in shared memory (int32)
 constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
 constexpr int SK_APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
+constexpr int SK_BREP = 16;                     // streamed-B mode: replicas of the pre-split planes in global memory (CTA b reads
+                                                // replica b % SK_BREP, so that 148 SMs do not hammer the same 64 L2 lines at once)
 constexpr int SK_BST = 4;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
 constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + 2 * SK_BST;
 constexpr int SK_BUDGET = 227 * 1024;
@@ -692,6 +695,7 @@ struct StemTcArgs {
     int32_t additive;         // pos[row*N + col] == pos[row*N] + pos[col] - pos[0]
     int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
     int32_t off_stg, off_tab, off_run, off_apl, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
+    int64_t brep_stride;      // streamed-B mode: byte distance between the SK_BREP replicas of the pre-split planes
     const uint8_t* bplanes;   // streamed-B mode: pre-split planes of this pass in global memory, [kb][hi|lo][2*NT rows x 32 B]
     TabRef bn, bk;
     const int64_t* hi;        // [M/128]
@@ -997,29 +1001,35 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         __syncwarp();
     } else {
         // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile ----
-        int rs = 0, bs = 0;
-        uint32_t rphase = 0, bphase = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const float2* src = p.A + t * TC_BM;
-            for (uint32_t kb = 0; kb < nkb; kb++) {
-                if (BSTREAM) {
-                    mbar_wait(b_empty(bs), bphase ^ 1);
-                    if (lane == 8) {
-                        mbar_expect_tx(b_full(bs), 2 * B_KB);
-                        bulk_g2s(smem_u32(smem + bs * 2 * B_KB), p.bplanes + (size_t)kb * 2 * B_KB, 2 * B_KB, b_full(bs));
-                    }
-                    if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
-                }
-                mbar_wait(raw_empty(rs), rphase ^ 1);
-                if (lane == 0) mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
-                __syncwarp();
-                if (lane < 8) {
+        // lanes 0-7 and lane 8 run INDEPENDENT loops (divergent on purpose): the A ring may run ahead of the (shallower)
+        // B ring by its full depth — the bytes of A in flight are what hides the HBM latency
+        if (lane < 8) {
+            int rs = 0;
+            uint32_t rphase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const float2* src = p.A + t * TC_BM;
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    mbar_wait(raw_empty(rs), rphase ^ 1);
+                    if (lane == 0) mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
+                    __syncwarp(0xffu);
                     const uint32_t dst = smem_u32(smem + p.off_raw + rs * SK_RAW_STAGE + lane * TC_BM * 8);
                     bulk_g2s(dst, src + (int64_t)(kb * TC_BK + lane) * p.lda, TC_BM * 8, raw_full(rs));
+                    if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
                 }
-                if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
             }
+        } else if (BSTREAM && lane == 8) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            const uint8_t* bsrc = p.bplanes + (size_t)(blockIdx.x % SK_BREP) * p.brep_stride;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+                for (uint32_t kb = 0; kb < nkb; kb++) {
+                    mbar_wait(b_empty(bs), bphase ^ 1);
+                    mbar_expect_tx(b_full(bs), 2 * B_KB);
+                    bulk_g2s(smem_u32(smem + bs * 2 * B_KB), bsrc + (size_t)kb * 2 * B_KB, 2 * B_KB, b_full(bs));
+                    if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                }
         }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -1033,8 +1043,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
 template <int NT>
 __global__ void stem_bsplit_kernel(const float2* __restrict__ B, TabRef bn, TabRef bk, int N, int conjB, uint8_t* __restrict__ out) {
     constexpr int B_KB = 2 * NT * TC_BK * 4;
-    const uint32_t kb = blockIdx.x, pass = blockIdx.y, nkb = gridDim.x;
-    uint8_t* dst = out + ((size_t)pass * nkb + kb) * 2 * B_KB;
+    const uint32_t kb = blockIdx.x, pass = blockIdx.y, nkb = gridDim.x, npass = gridDim.y;
+    uint8_t* dst = out + (((size_t)blockIdx.z * npass + pass) * nkb + kb) * 2 * B_KB;   // replica z
     for (uint32_t u = threadIdx.x; u < (uint32_t)NT * 2; u += blockDim.x) {
         const uint32_t row = u % NT, kc = u / NT;
         float2 v[4];
@@ -1051,7 +1061,7 @@ template <int NT, bool BSTREAM>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     // four plane stages (a worker group refills one while the tensor core reads its other one) if that still leaves
     // >= 5 raw stages (40 KB of bulk copies in flight), else two
-    if (sk_layout(NT, a, 4) < 5) sk_layout(NT, a, 2);
+    if (getenv("TNB_SK_PL2") || sk_layout(NT, a, 4) < 5) sk_layout(NT, a, 2);
     if (a.raw_stages < 3) return -1;
     const int smem = a.off_bar + SK_NBARS * 8 + 16;
     TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
@@ -1136,7 +1146,7 @@ bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
 // workspace (in complex64 elements) the streamed-B mode needs for `npass` passes of `Nsmall` columns; 0 = resident mode
 int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass) {
     if (Nsmall * K * 16 <= 64 * 1024) return 0;
-    return npass * (K / TC_BK) * (128 * Nsmall) / 8;
+    return SK_BREP * npass * (K / TC_BK) * (128 * Nsmall) / 8;
 }
 
 // returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back).
@@ -1160,11 +1170,12 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass)
         const int nkb = e.K / TC_BK;
         const size_t pass_bytes = (size_t)nkb * 128 * 64;
         if (e.n0 == 0) {
-            stem_bsplit_kernel<64><<<dim3(nkb, npass), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
+            stem_bsplit_kernel<64><<<dim3(nkb, npass, SK_BREP), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
             ctx->launches++;
             TNB_CUDA_CHECK(ctx, cudaGetLastError());
         }
         a.bplanes = (const uint8_t*)ws + (size_t)(e.n0 / 64) * pass_bytes;
+        a.brep_stride = (int64_t)npass * pass_bytes;
         return launch_stem_tc<64, true>(ctx, a);
     }
     if (e.N <= 16) return launch_stem_tc<16, false>(ctx, a);
