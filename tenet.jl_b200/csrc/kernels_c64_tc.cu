@@ -52,6 +52,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a CONVERGED warp: the MMA-issue loops run warp-uniform and only the tcgen05.mma / commit are predicated on
+// this, so ptxas emits straight-line UTCHMMA code (an `if (lane == 0)` region makes it wrap every MMA in an
+// ELECT / BRA.U.ANY serialisation loop: ~250 SASS instructions per k-block from one thread, which paced the kernels)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -282,8 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) c64_tf32x3_kernel(const TcArgs 
         }
         tc_fence_before();
     } else {
-        // ===================== MMA issuer (warp 8) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp 8): warp-uniform loop, one elected lane issues =====================
+        {
             constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
             const uint32_t d_re = tmem_base, d_im = tmem_base + NT;
             int stage = 0;
@@ -298,24 +306,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) c64_tf32x3_kernel(const TcArgs 
                 const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + S::B_PLANE),
                                b_ih = make_smem_desc(sb + 2 * S::B_PLANE), b_il = make_smem_desc(sb + 3 * S::B_PLANE);
                 const uint32_t acc = kb > 0 ? 1u : 0u;
-                // Cre = Are.Bre - Aim.Bim     (small cross terms first, hi*hi last)
-                umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
-                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
-                umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                // Cim = Are.Bim + Aim.Bre
-                umma_tf32(d_im, a_rh, b_il, IDESC, acc);
-                umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
-                umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
-                umma_commit(empty_bar(stage));     // implies tcgen05.fence::before_thread_sync
+                if (elect_one()) {
+                    // Cre = Are.Bre - Aim.Bim     (small cross terms first, hi*hi last)
+                    umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
+                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                    // Cim = Are.Bim + Aim.Bre
+                    umma_tf32(d_im, a_rh, b_il, IDESC, acc);
+                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                    umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_commit(empty_bar(stage));     // implies tcgen05.fence::before_thread_sync
+                    if (kb + 1 == nkb) umma_commit(acc_bar);
+                }
+                __syncwarp();
                 if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(acc_bar);
         }
         __syncwarp();
     }
@@ -558,18 +569,15 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         }
     } else if (warp == 16) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        // ---- MMA issuer ----
-        if (lane == 0) {
+        // ---- MMA issuer: warp-uniform loop, one elected lane issues (see elect_one) ----
+        {
             constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
             int ps = 0;
             uint32_t pphase = 0;
             for (uint32_t kb = 0; kb < nkb; kb++) {
                 const uint32_t c = kb / ACC_KCB, set = c & 1;
                 const bool first = (kb % ACC_KCB) == 0;
-                if (first && c >= 2) {
-                    mbar_wait(accempty_bar(set), ((c >> 1) - 1) & 1);
-                    tc_fence_after();
-                }
+                if (first && c >= 2) mbar_wait(accempty_bar(set), ((c >> 1) - 1) & 1);
                 mbar_wait(pl_full(ps), pphase);
                 tc_fence_after();
                 const uint32_t d_re = tmem_base + set * 256u, d_im = d_re + 128u;
@@ -580,20 +588,23 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
                 const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + S::B_PLANE),
                                b_ih = make_smem_desc(sb + 2 * S::B_PLANE), b_il = make_smem_desc(sb + 3 * S::B_PLANE);
                 const uint32_t acc = first ? 0u : 1u;
-                umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
-                umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
-                umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                umma_tf32(d_im, a_rh, b_il, IDESC, acc);
-                umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
-                umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
-                umma_commit(pl_empty(ps));
-                if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(set));
+                if (elect_one()) {
+                    umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
+                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
+                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                    umma_tf32(d_im, a_rh, b_il, IDESC, acc);
+                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
+                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
+                    umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
+                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_commit(pl_empty(ps));
+                    if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(set));
+                }
+                __syncwarp();
                 if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
             }
         }
@@ -645,39 +656,42 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 64, K <= 128.
+// Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 64 per pass, K <= 128.
 //
-// These steps carry most of the BYTES of a good sliced path (arithmetic intensity 13-43 flop/B, below the ridge), so
-// the kernel is organised around HBM, not around the tensor pipe:
+// These steps carry most of the BYTES of a good sliced path (arithmetic intensity 13-64 flop/B, around the ridge).
+// Round-1 profiling (profiles/r1_summary.md) showed the first version of this kernel was bound by SHARED-MEMORY
+// bandwidth, not by HBM or the tensor pipe: a 128 x 128 x 8 tf32 MMA with both operands in shared memory reads
+// 8 KB per 64 clk = the whole 128 B/clk of the SM, and the 3xTF32 split re-reads every A plane up to twice.  So:
 //   * one persistent CTA per SM walks 128-row tiles of the big operand; its A tile rows arrive by cp.async.bulk
 //     (8 KB per 8 k) into a raw ring, every A byte is read from HBM exactly once;
-//   * the small operand is gathered, split (hi/lo) and laid out ONCE per CTA for all of K as two resident UMMA
-//     planes P_hi, P_lo of 2N rows each: rows [0,N) hold B_re, rows [N,2N) hold B_im.  One MMA of width 2N then
-//     produces [X.B_re | X.B_im] for an A plane X, so a k-block costs 6 MMAs instead of 12 — a 128 x n x 8 tf32 MMA
-//     costs ~46 clk for every n <= 64 (the 4 KB A read from shared memory, measured by tools/probes/mma_probe.cu), so
-//     halving the MMA count halves the tensor-pipe time of the small-N steps:
-//         F = A_re.B  (A_rh.P_lo + A_rl.P_hi + A_rh.P_hi)        E = A_im.B  (A_ih.P_lo + A_il.P_hi + A_ih.P_hi)
-//         C_re = F[0:N] - E[N:2N]      C_im = F[N:2N] + E[0:N]     (combined by the epilogue warps in FP32)
-//   * 8 worker warps split the raw A tiles into planes, one thread issues the MMAs into one of two TMEM sets
-//     (4N columns each);
-//   * 8 epilogue warps drain the other set (tcgen05.ld), drop each value at the RANK of its output address inside
-//     the tile's (tile-invariant, planner-sorted) address pattern in a shared staging tile, and write the tile to C
-//     in ascending address order, two elements (16 B) per thread — coalesced whatever layout the consumer asked for.
-//     When the rank is additive, rank(row, col) = r(row) + c(col) (always the case for power-of-two extents), it is
-//     computed from one register and a broadcast column table instead of a per-element table lookup.
-//     Drain of tile i overlaps the copies, splits and MMAs of tile i+1.
-// Chain length in TMEM is 3*K/8 <= 48 MMAs per accumulator (K <= 128): the round-toward-zero bias stays ~3e-6 relative.
+//   * 8 worker warps read the raw tile once, split it (re/im, hi/lo) in registers and store the four A planes into
+//     TENSOR MEMORY (tcgen05.st, lane = row, 8 columns per plane per k-block, 4-stage ring of 32 columns): the MMAs
+//     take A from TMEM (".ts" form), so the A planes cost no shared-memory bandwidth at all and need no proxy fence;
+//   * the small operand is split (hi/lo) ONCE per CTA for all of K into two resident UMMA planes P_hi, P_lo of 2N
+//     rows each (rows [0,N) = B_re, rows [N,2N) = B_im) — or, when N*K*16 > 64 KB, once per launch into global memory
+//     by a tiny pre-pass and streamed per k-block through a 4-stage ring (one 8 KB bulk copy, L2-resident source);
+//   * MMA forms (a 128 x n x 8 tf32 MMA costs max(45.5, n/2) clk, SS or TS: tools/probes/mma_probe.cu, ts_probe.cu):
+//       N <= 32: 6 MMAs of width 2N per k-block into F = A_re.[B_re|B_im], E = A_im.[B_re|B_im]  (4N TMEM columns per
+//                set); the epilogue forms C_re = F[0:N] - E[N:2N], C_im = F[N:2N] + E[0:N];
+//       N  = 64: 12 MMAs of width 64 into C_re | C_im directly (a_negate for the -A_im.B_im terms; 2N columns per
+//                set) — F/E would need 2 x 256 accumulator columns and leave no room for the A ring;
+//   * two accumulator sets: 8 epilogue warps drain one (tcgen05.ld) while the MMAs fill the other, drop each value
+//     at the RANK of its output address inside the tile's (tile-invariant, planner-sorted) address pattern in a
+//     shared staging tile, and write the tile to C in ascending address order, 16 B per thread — coalesced whatever
+//     layout the consumer asked for.  When the rank is separable on disjoint bits, rank(row,col) = r(row) ^ c(col)
+//     (always for power-of-two extents), it comes from one register and a broadcast column table.
+// Chain length in TMEM is <= 6*K/8 = 96 MMAs per accumulator (K <= 128): round-toward-zero bias ~6e-6 relative.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SK_WORKERS = 256;                 // warps 0-7
 constexpr int SK_EPI = 256;                     // warps 8-15: two per TMEM lane quarter, each takes half of the columns
 constexpr int SK_THREADS = SK_WORKERS + SK_EPI + 64;   // + MMA warp 16, copy warp 17
-constexpr int SK_PL_MAX = 4;                    // A plane stages (16 KB each): 4 when the smem budget allows, else 2
+constexpr int SK_PL_MAX = 4;                    // A plane stages in tensor memory (32 columns each)
 constexpr int SK_RAW_MAX = 16;                  // raw A stages (8 KB each): as many as shared memory allows — the
                                                 // bytes in flight per SM (>= 40 KB) are what saturates HBM
 constexpr int SK_RUNS_MAX = 1024;               // run bases kept in shared memory (int32)
 constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
-constexpr int SK_APL_STAGE = 4 * TC_BM * TC_BK * 4;        // 16 KB
-constexpr int SK_BREP = 16;                     // streamed-B mode: replicas of the pre-split planes in global memory (CTA b reads
+constexpr int SK_APL_COLS = 4 * TC_BK;                     // TMEM columns of one A stage: planes rh | rl | ih | il, 8 k each
+constexpr int SK_BREP = 1;                      // streamed-B mode: replicas of the pre-split planes in global memory (CTA b reads
                                                 // replica b % SK_BREP, so that 148 SMs do not hammer the same 64 L2 lines at once)
 constexpr int SK_BST = 4;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
 constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + 2 * SK_BST;
@@ -690,11 +704,10 @@ struct StemTcArgs {
     int64_t M, lda;
     int32_t N, K, n0, conjA, conjB;
     int32_t raw_stages;       // chosen by the launcher from the shared-memory budget
-    int32_t pl_stages;        // 2 or 4 A-plane stages
     int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
     int32_t additive;         // pos[row*N + col] == pos[row*N] + pos[col] - pos[0]
     int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
-    int32_t off_stg, off_tab, off_run, off_apl, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
+    int32_t off_stg, off_tab, off_run, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
     int64_t brep_stride;      // streamed-B mode: byte distance between the SK_BREP replicas of the pre-split planes
     const uint8_t* bplanes;   // streamed-B mode: pre-split planes of this pass in global memory, [kb][hi|lo][2*NT rows x 32 B]
     TabRef bn, bk;
@@ -704,19 +717,17 @@ struct StemTcArgs {
     float alpha[2], beta[2];
 };
 
-// shared-memory map: [ B planes | staging tile | rank table(s) | run bases | A planes ring | raw ring | barriers, tmem slot ]
-__host__ inline int sk_layout(int nt, StemTcArgs& a, int pl) {
+// shared-memory map: [ B planes (resident or 4-stage ring) | staging tile | rank table | run bases | raw ring | barriers, tmem slot ]
+__host__ inline int sk_layout(int nt, StemTcArgs& a) {
     auto up = [](int x, int q) { return (x + q - 1) / q * q; };
     const int nkb = a.K / TC_BK;
     const int nruns = (TC_BM * a.N) >> a.run_shift;
     a.off_stg = up((a.bplanes ? SK_BST : nkb) * nt * 128, 1024);
     a.off_tab = a.off_stg + up(TC_BM * a.N * 8, 1024);
     a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
-    a.off_apl = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
-    a.off_raw = a.off_apl + pl * SK_APL_STAGE;
+    a.off_raw = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
     int raw = (SK_BUDGET - (SK_NBARS * 8 + 16) - a.off_raw) / SK_RAW_STAGE;
     if (raw > SK_RAW_MAX) raw = SK_RAW_MAX;
-    a.pl_stages = pl;
     a.raw_stages = raw;
     a.off_bar = a.off_raw + (raw > 0 ? raw : 0) * SK_RAW_STAGE;
     return raw;
@@ -744,19 +755,40 @@ __device__ __forceinline__ void split_store_b(uint8_t* kb_base, int plane_bytes,
 // conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
 __device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, A operand in tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // BSTREAM: the small operand's planes do not fit in shared memory (N*K*16 > 64 KB): a tiny pre-pass
-// (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and the copy warp streams one
-// 2*B_KB stage per k-block (one bulk copy, L2-resident source) next to the A rows.
-template <int NT, bool BSTREAM>   // NT: columns of the small operand per launch, padded (16, 32, 64); UMMA N = 2*NT
+// (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and lane 8 of the copy warp
+// streams one 2*B_KB stage per k-block (one bulk copy, L2-resident source) next to the A rows.
+template <int NT, bool BSTREAM>   // NT: columns of the small operand per launch, padded (16, 32, 64)
 __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nkb = (uint32_t)p.K / TC_BK;
     const int64_t ntiles = p.M / TC_BM;
+    constexpr bool F6 = NT <= 32;                                    // 6 wide MMAs into F/E, else 12 into re/im
     constexpr int B_KB = 2 * NT * TC_BK * 4;                         // bytes of one B plane ([re | im] rows) per k-block
-    const uint32_t b_plane = nkb * B_KB;                             // bytes of one B plane (all k)
+    const uint32_t b_plane = nkb * B_KB;                             // bytes of one B plane (all k), resident mode
 
-    const int SK_RAW = p.raw_stages, SK_PL = p.pl_stages;
+    const int SK_RAW = p.raw_stages;
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(smem + p.off_tab); // general: swizzled rank of (col, row)
     uint32_t* tab32 = reinterpret_cast<uint32_t*>(smem + p.off_tab); // additive: swizzled staging byte offset of column c [NT]
     int32_t* runbase = reinterpret_cast<int32_t*>(smem + p.off_run);
@@ -772,12 +804,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     auto b_full = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + s); };
     auto b_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + SK_BST + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + SK_NBARS * 8);
-    constexpr uint32_t SET_COLS = 4 * NT;                            // F = [A_re.B_re | A_re.B_im], E = [A_im.B_re | A_im.B_im]
-    constexpr uint32_t TMEM_COLS = 2 * SET_COLS;                     // 128 / 256 / 512
+    constexpr uint32_t SET_COLS = F6 ? 4 * NT : 2 * NT;              // F | E (2N each), or re | im (N each)
+    constexpr uint32_t APL_COL0 = 2 * SET_COLS;                      // A plane ring behind the two accumulator sets
+    constexpr uint32_t USED_COLS = APL_COL0 + SK_PL_MAX * SK_APL_COLS;
+    constexpr uint32_t TMEM_COLS = USED_COLS <= 256 ? 256 : 512;
 
     if (tid == 0) {
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
-        for (int s = 0; s < SK_PL; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
+        for (int s = 0; s < SK_PL_MAX; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32); }
         for (int s = 0; s < SK_BST; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -821,36 +855,42 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
-        // ---- workers: raw A tile -> planes.  Two groups of 4 warps take alternate k-blocks (group = parity of the
-        // global k-block counter = plane stage), so two latency chains (wait, LDS, split, STS, proxy fence, arrive)
-        // run concurrently; a thread owns one row and both 4-k halves of its k-block. ----
+        // ---- workers: raw A tile -> four planes in TENSOR MEMORY.  Two groups of 4 warps take alternate k-blocks
+        // (group = parity of the global k-block counter), so two latency chains (wait, LDS, split, tcgen05.st, arrive)
+        // run concurrently; a thread owns one row (= its TMEM lane) and all 8 k of its k-block. ----
         const int group = warp >> 2, prow = tid & 127;
         const int raw_row = p.off_raw + prow * 8;
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + APL_COL0;
         int64_t my_tiles = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) my_tiles++;
         const uint64_t total_kb = (uint64_t)my_tiles * nkb;
         for (uint64_t g = group; g < total_kb; g += 2) {
             const int rs = (int)(g % (uint64_t)SK_RAW);
-            const int ps = (int)(g % (uint64_t)SK_PL);          // group g%2 owns stages {group, group+2}
-            const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g / (uint64_t)SK_PL) & 1);
+            const int ps = (int)(g % (uint64_t)SK_PL_MAX);      // group g%2 owns stages {group, group+2}
+            const uint32_t rphase = (uint32_t)((g / (uint64_t)SK_RAW) & 1), pphase = (uint32_t)((g / (uint64_t)SK_PL_MAX) & 1);
             mbar_wait(raw_full(rs), rphase);
-            float2 v0[4], v1[4];
             const uint8_t* raw = smem + rs * SK_RAW_STAGE + raw_row;
+            uint32_t pl[32];                                     // rh[8] | rl[8] | ih[8] | il[8]
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
-                v1[i] = *reinterpret_cast<const float2*>(raw + (4 + i) * TC_BM * 8);
+            for (int i = 0; i < 8; i++) {
+                const float2 v = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                const float re = v.x, im = p.conjA ? -v.y : v.y;
+                const float rh = tf32_hi(re), ih = tf32_hi(im);
+                pl[i] = __float_as_uint(rh); pl[8 + i] = __float_as_uint(re - rh);
+                pl[16 + i] = __float_as_uint(ih); pl[24 + i] = __float_as_uint(im - ih);
             }
-            mbar_wait(apl_empty(ps), pphase ^ 1);
-            uint8_t* pl = smem + p.off_apl + ps * SK_APL_STAGE;
-            split_store(pl, TC_BM * TC_BK * 4, prow, 0, v0, p.conjA);
-            split_store(pl, TC_BM * TC_BK * 4, prow, 1, v1, p.conjA);
-            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(apl_full(ps)); mbar_arrive(raw_empty(rs)); }
+            if (lane == 0) mbar_arrive(raw_empty(rs));          // raw stage consumed (values are in registers)
+            mbar_wait(apl_empty(ps), pphase ^ 1);
+            tc_fence_after();
+            tmem_st32(lane_base + ps * SK_APL_COLS, pl);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(apl_full(ps));
         }
     } else if (warp < 16) {
-        // ---- epilogue warps: TMEM -> combine -> staging (rank order) -> C (ascending addresses) ----
+        // ---- epilogue warps: TMEM -> (combine) -> staging (rank order) -> C (ascending addresses) ----
         const int q = warp & 3, half = (warp - 8) >> 2;
         const int etid = tid - SK_WORKERS;                         // 0..255
         const uint32_t row = q * 32 + lane;
@@ -883,11 +923,24 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * SET_COLS;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                    uint32_t fr[16], fi[16], er[16], ei[16];
-                    tmem_ld16(taddr + c0, fr);
-                    tmem_ld16(taddr + NT + c0, fi);
-                    tmem_ld16(taddr + 2 * NT + c0, er);
-                    tmem_ld16(taddr + 3 * NT + c0, ei);
+                    uint32_t xr[16], xi[16];
+                    if (F6) {
+                        uint32_t er[16], ei[16];
+                        tmem_ld16(taddr + c0, xr);               // A_re.B_re
+                        tmem_ld16(taddr + NT + c0, xi);          // A_re.B_im
+                        tmem_ld16(taddr + 2 * NT + c0, er);      // A_im.B_re
+                        tmem_ld16(taddr + 3 * NT + c0, ei);      // A_im.B_im
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            xr[j] = __float_as_uint(__uint_as_float(xr[j]) - __uint_as_float(ei[j]));
+                            xi[j] = __float_as_uint(__uint_as_float(xi[j]) + __uint_as_float(er[j]));
+                        }
+                    } else {
+                        tmem_ld16(taddr + c0, xr);
+                        tmem_ld16(taddr + NT + c0, xi);
+                        tmem_ld_wait();
+                    }
                     if (additive) {
                         uint32_t co[16];
 #pragma unroll
@@ -895,17 +948,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                             const uint4 c4 = *reinterpret_cast<const uint4*>(tab32 + c0 + j);
                             co[j] = c4.x; co[j + 1] = c4.y; co[j + 2] = c4.z; co[j + 3] = c4.w;
                         }
-                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; j++)
-                            *reinterpret_cast<float2*>(stg_b + (rowoff ^ co[j])) =
-                                make_float2(__uint_as_float(fr[j]) - __uint_as_float(ei[j]), __uint_as_float(fi[j]) + __uint_as_float(er[j]));
+                            *reinterpret_cast<float2*>(stg_b + (rowoff ^ co[j])) = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
                     } else {
-                        tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 16; j++)
-                            stg[tab16[(c0 + j) * TC_BM + row]] =
-                                make_float2(__uint_as_float(fr[j]) - __uint_as_float(ei[j]), __uint_as_float(fi[j]) + __uint_as_float(er[j]));
+                            stg[tab16[(c0 + j) * TC_BM + row]] = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
                     }
                 }
             }
@@ -962,47 +1011,66 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile free again
         }
     } else if (warp == 16) {
-        // ---- MMA issuer: 6 MMAs of width 2*NT per k-block; descriptors differ only in their 14-bit address field ----
-        if (lane == 0) {
-            constexpr uint32_t IDESC = make_idesc<2 * NT>(false);
-            constexpr uint64_t AP16 = (TC_BM * TC_BK * 4) >> 4;
-            const uint64_t adesc0 = make_smem_desc(smem_u32(smem + p.off_apl));
+        // ---- MMA issuer: A planes from tensor memory, B planes from shared memory.  The whole warp runs the loop
+        // (waits included); one elected lane issues the MMAs and commits. ----
+        {
+            constexpr uint32_t IDESC6 = make_idesc<2 * NT>(false);
+            constexpr uint32_t IDESC = make_idesc<NT>(false), IDESC_NEG = make_idesc<NT>(true);
             const uint64_t bdesc0 = make_smem_desc(smem_u32(smem));
             const uint64_t bl_off = BSTREAM ? (uint64_t)(B_KB >> 4) : (uint64_t)(b_plane >> 4);
+            constexpr uint64_t IM_OFF = (uint64_t)(NT * TC_BK * 4) >> 4;   // rows [N, 2N) of a plane = B_im
+            const uint32_t a0 = tmem_base + APL_COL0;
             int ps = 0, bs = 0;
             uint32_t pphase = 0, bphase = 0, i = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
                 const uint32_t set = i & 1;
-                if (i >= 2) { mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1); tc_fence_after(); }
-                const uint32_t d_f = tmem_base + set * SET_COLS, d_e = d_f + 2 * NT;
+                if (i >= 2) mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1);
+                const uint32_t d0 = tmem_base + set * SET_COLS;
                 for (uint32_t kb = 0; kb < nkb; kb++) {
+                    if (BSTREAM) mbar_wait(b_full(bs), bphase);
                     mbar_wait(apl_full(ps), pphase);
                     tc_fence_after();
-                    const uint64_t a_rh = adesc0 + (uint64_t)(ps * (SK_APL_STAGE >> 4));
-                    if (BSTREAM) { mbar_wait(b_full(bs), bphase); tc_fence_after(); }
+                    const uint32_t a_rh = a0 + ps * SK_APL_COLS, a_rl = a_rh + 8, a_ih = a_rh + 16, a_il = a_rh + 24;
                     const uint64_t b_h = bdesc0 + (uint64_t)((BSTREAM ? 2u * bs : kb) * (B_KB >> 4)), b_l = b_h + bl_off;
                     const uint32_t acc = kb > 0 ? 1u : 0u;
-                    umma_tf32(d_f, a_rh, b_l, IDESC, acc);
-                    umma_tf32(d_f, a_rh + AP16, b_h, IDESC, 1u);
-                    umma_tf32(d_f, a_rh, b_h, IDESC, 1u);
-                    umma_tf32(d_e, a_rh + 2 * AP16, b_l, IDESC, acc);
-                    umma_tf32(d_e, a_rh + 3 * AP16, b_h, IDESC, 1u);
-                    umma_tf32(d_e, a_rh + 2 * AP16, b_h, IDESC, 1u);
-                    umma_commit(apl_empty(ps));
-                    if (++ps == SK_PL) { ps = 0; pphase ^= 1; }
-                    if (BSTREAM) {
-                        umma_commit(b_empty(bs));
-                        if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                    if (elect_one()) {
+                        if (F6) {
+                            const uint32_t d_f = d0, d_e = d0 + 2 * NT;
+                            umma_tf32_ts(d_f, a_rh, b_l, IDESC6, acc);
+                            umma_tf32_ts(d_f, a_rl, b_h, IDESC6, 1u);
+                            umma_tf32_ts(d_f, a_rh, b_h, IDESC6, 1u);
+                            umma_tf32_ts(d_e, a_ih, b_l, IDESC6, acc);
+                            umma_tf32_ts(d_e, a_il, b_h, IDESC6, 1u);
+                            umma_tf32_ts(d_e, a_ih, b_h, IDESC6, 1u);
+                        } else {
+                            const uint32_t d_re = d0, d_im = d0 + NT;
+                            const uint64_t b_rh = b_h, b_ih = b_h + IM_OFF, b_rl = b_l, b_il = b_l + IM_OFF;
+                            umma_tf32_ts(d_re, a_rh, b_rl, IDESC, acc);
+                            umma_tf32_ts(d_re, a_rl, b_rh, IDESC, 1u);
+                            umma_tf32_ts(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                            umma_tf32_ts(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                            umma_tf32_ts(d_re, a_rh, b_rh, IDESC, 1u);
+                            umma_tf32_ts(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                            umma_tf32_ts(d_im, a_rh, b_il, IDESC, acc);
+                            umma_tf32_ts(d_im, a_rl, b_ih, IDESC, 1u);
+                            umma_tf32_ts(d_im, a_ih, b_rl, IDESC, 1u);
+                            umma_tf32_ts(d_im, a_il, b_rh, IDESC, 1u);
+                            umma_tf32_ts(d_im, a_rh, b_ih, IDESC, 1u);
+                            umma_tf32_ts(d_im, a_ih, b_rh, IDESC, 1u);
+                        }
+                        umma_commit(apl_empty(ps));
+                        if (BSTREAM) umma_commit(b_empty(bs));
+                        if (kb + 1 == nkb) umma_commit(accfull_bar(set));
                     }
+                    __syncwarp();
+                    if (++ps == SK_PL_MAX) { ps = 0; pphase ^= 1; }
+                    if (BSTREAM && ++bs == SK_BST) { bs = 0; bphase ^= 1; }
                 }
-                umma_commit(accfull_bar(set));
             }
         }
-        __syncwarp();
     } else {
-        // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile ----
-        // lanes 0-7 and lane 8 run INDEPENDENT loops (divergent on purpose): the A ring may run ahead of the (shallower)
-        // B ring by its full depth — the bytes of A in flight are what hides the HBM latency
+        // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile; lane 8 streams the B planes.
+        // The two loops are INDEPENDENT (divergent on purpose): the A ring runs ahead by its full depth. ----
         if (lane < 8) {
             int rs = 0;
             uint32_t rphase = 0;
@@ -1059,10 +1127,7 @@ __global__ void stem_bsplit_kernel(const float2* __restrict__ B, TabRef bn, TabR
 
 template <int NT, bool BSTREAM>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
-    // four plane stages (a worker group refills one while the tensor core reads its other one) if that still leaves
-    // >= 5 raw stages (40 KB of bulk copies in flight), else two
-    if (getenv("TNB_SK_PL2") || sk_layout(NT, a, 4) < 5) sk_layout(NT, a, 2);
-    if (a.raw_stages < 3) return -1;
+    if (sk_layout(NT, a) < 3) return -1;
     const int smem = a.off_bar + SK_NBARS * 8 + 16;
     TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
     int64_t grid = a.M / TC_BM;
