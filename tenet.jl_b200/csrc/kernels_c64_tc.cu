@@ -110,6 +110,30 @@ __host__ __device__ constexpr uint32_t make_idesc(bool neg_a) {
            | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, A operand in tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // x_hi = x with the low 13 mantissa bits cleared (what the tensor core would read anyway), x_lo = x - x_hi exactly.
 // One LOP3 instead of the multi-instruction emulation of cvt.rna.tf32 on sm_100a; the split stays error-free and
 // x_lo (<= 2^-10 |x|) is truncated to TF32 by the MMA, leaving a representation error <= 2^-21 |x|.
@@ -172,6 +196,22 @@ __device__ __forceinline__ void split_store(uint8_t* plane0, int plane_bytes, in
     *reinterpret_cast<float4*>(plane0 + plane_bytes + off) = make_float4(rl[0], rl[1], rl[2], rl[3]);
     *reinterpret_cast<float4*>(plane0 + 2 * plane_bytes + off) = make_float4(ih[0], ih[1], ih[2], ih[3]);
     *reinterpret_cast<float4*>(plane0 + 3 * plane_bytes + off) = make_float4(il[0], il[1], il[2], il[3]);
+}
+
+// 4 consecutive k of this thread's row (= its TMEM lane) -> planes rh | rl | ih | il, 8 columns apart, of a TMEM A stage
+__device__ __forceinline__ void split_store_tmem(uint32_t taddr, const float2 v[4], int conj) {
+    uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float re = v[i].x, im = conj ? -v[i].y : v[i].y;
+        const float h = tf32_hi(re), g = tf32_hi(im);
+        rh[i] = __float_as_uint(h); rl[i] = __float_as_uint(re - h);
+        ih[i] = __float_as_uint(g); il[i] = __float_as_uint(im - g);
+    }
+    tmem_st4(taddr, rh[0], rh[1], rh[2], rh[3]);
+    tmem_st4(taddr + 8, rl[0], rl[1], rl[2], rl[3]);
+    tmem_st4(taddr + 16, ih[0], ih[1], ih[2], ih[3]);
+    tmem_st4(taddr + 24, il[0], il[1], il[2], il[3]);
 }
 
 template <int NT>
@@ -353,12 +393,17 @@ int launch_tc(tnb_ctx* ctx, const TcArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Chunked-accumulation variant (the default): same data path, 128 x 128 tile, but the TMEM accumulators only
-// ever hold a CHUNK of KCB k-blocks.  The tensor core adds into its FP32 accumulator with round-toward-zero, a
-// bias that grows linearly with the number of chained MMAs (measured: ~6e-8 * #MMAs relative, i.e. 1.5e-5 at
-// K = 1024 when the whole K is chained — see profiles/r1_tc_accuracy.md).  Here two TMEM accumulator sets
-// ping-pong: while the MMA warp fills one with chunk c+1, the 16 worker warps drain chunk c with tcgen05.ld and
-// add it into per-thread FP32 totals with round-to-nearest.  Chain length = 6*KCB MMAs => ~3e-6 relative.
+// Chunked-accumulation variant (the default GEMM kernel): 128 x 128 tile; the TMEM accumulators only ever hold a
+// CHUNK of KCB k-blocks.  The tensor core adds into its FP32 accumulator with round-toward-zero, a bias that grows
+// linearly with the number of chained MMAs (measured: ~6e-8 * #MMAs relative, i.e. 1.5e-5 at K = 1024 when the whole
+// K is chained).  After every chunk the 16 worker warps drain the accumulators with tcgen05.ld (measured 394 B/clk/SM:
+// ~350 clk for the 128 KB, tools/probes/ldtm_probe.cu) and add them into per-thread FP32 totals with round-to-nearest.
+// Chain length = 6*KCB = 96 MMAs => ~6e-6 relative.
+// The A planes go to TENSOR MEMORY (tcgen05.st by the workers, ".ts" MMAs): with both operands in shared memory a
+// 128x128x8 tf32 MMA reads 8 KB per 64 clk = all of the SM's 128 B/clk, and the split planes plus the raw ring pushed
+// the kernel to 168 KB of shared-memory traffic per k-block (1312 clk) against 768 clk of MMA time — it was
+// shared-memory bound at ~0.8 of the tensor peak.  With A in TMEM: 96 KB per k-block.  That leaves room for ONE
+// accumulator set (256 columns) next to the 8-stage A ring (256 columns); the drain bubble is ~3 % of a chunk.
 //
 //   warps 0-15 workers: (a) producers, one (row, 4k) unit per thread and k-block (warps 0-7 feed A, 8-15 feed B),
 //                       (b) every KCB k-blocks drain the finished chunk into 64 total registers
@@ -368,14 +413,16 @@ int launch_tc(tnb_ctx* ctx, const TcArgs& a) {
 constexpr int ACC_NT = 128;
 constexpr int ACC_WORKERS = 512;              // warps 0-15
 constexpr int ACC_THREADS = ACC_WORKERS + 128; // + warpgroup 4: warp 16 MMA issuer, warp 17 bulk-copy issuer, 18-19 idle
-constexpr int ACC_KCB = 8;                    // k-blocks (of 8 complex k) per TMEM chunk
+constexpr int ACC_KCB = 16;                   // k-blocks (of 8 complex k) per TMEM chunk: chain of 96 MMAs per accumulator
 constexpr int ACC_RAW_STAGES = 6;             // raw (interleaved complex) operand tiles landed by cp.async.bulk
-constexpr int ACC_PL_STAGES = 4;              // split planes consumed by tcgen05.mma (workers fill them two at a time)
+constexpr int ACC_PL_STAGES = 8;              // split planes consumed by tcgen05.mma (workers fill them two at a time):
+                                              // B planes in shared memory, A planes in tensor memory (32 columns per stage)
+constexpr uint32_t ACC_APL_COL0 = 256;        // TMEM: columns [0,256) accumulators (re | im), [256,512) the A plane ring
 
 struct AccSmem {
     static constexpr int A_PLANE = TC_BM * TC_BK * 4;                  // 4 KB
     static constexpr int B_PLANE = ACC_NT * TC_BK * 4;
-    static constexpr int PL_STAGE = 4 * A_PLANE + 4 * B_PLANE;         // 32 KB
+    static constexpr int PL_STAGE = 4 * B_PLANE;                       // 16 KB (the A planes live in tensor memory)
     static constexpr int RAW_HALF = TC_BK * TC_BM * 8;                 // 8 KB: [8 k][128 rows] float2
     static constexpr int RAW_STAGE = 2 * RAW_HALF;                     // A then B
     static constexpr int RAW_OFF = ACC_PL_STAGES * PL_STAGE;
@@ -456,8 +503,8 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         const int u = feeds_a ? tid : tid - 256;
         const int prow = u & 127, pkc = u >> 7;
         const int pconj = feeds_a ? p.conjA : p.conjB;
-        const int plane_bytes = feeds_a ? S::A_PLANE : S::B_PLANE;
-        const int plane_base = feeds_a ? 0 : 4 * S::A_PLANE;
+        // A feeders: TMEM lane = row, columns of this thread's 4 k inside a stage: plane*8 + pkc*4
+        const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ACC_APL_COL0 + (uint32_t)(pkc * 4);
         const int raw_base = S::RAW_OFF + (feeds_a ? 0 : S::RAW_HALF) + (pkc * 4 * TC_BM + prow) * 8;
         const bool row_ok = (uint32_t)prow < (feeds_a ? mv : nv);
         const int q = warp & 3, g = warp >> 2;        // TMEM lane quarter, 32-column group
@@ -465,10 +512,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
 #pragma unroll
         for (int j = 0; j < 32; j++) { tr[j] = 0.f; ti[j] = 0.f; }
         auto drain = [&](uint32_t c) {
-            const uint32_t set = c & 1;
-            mbar_wait(accfull_bar(set), (c >> 1) & 1);
+            mbar_wait(accfull_bar(0), c & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(g * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 uint32_t r[16], im[16];
@@ -483,7 +529,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accempty_bar(set));
+            if (lane == 0) mbar_arrive(accempty_bar(0));
         };
 
         // Two k-blocks per iteration: one fence.proxy.async + one round of barrier traffic per 16 k, and twice the
@@ -492,9 +538,12 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         int rs = 0, ps = 0;
         uint32_t rphase = 0, pphase = 0, drained = 0;
         for (uint32_t kb = 0; kb < nkb; kb += 2) {
-            if (kb % ACC_KCB == 0) {
+            // single accumulator set: chunk c-1 must be drained before the MMAs of chunk c start.  Do it once the plane
+            // ring is primed with the first stages of chunk c (they only need MMAs of chunk c-1 to retire), so the
+            // tensor core restarts on ready stages right after the drain.
+            if (kb >= ACC_KCB && kb % ACC_KCB == ACC_PL_STAGES) {
                 const uint32_t c = kb / ACC_KCB;
-                while (drained + 2 <= c) { drain(drained); drained++; }
+                while (drained < c) { drain(drained); drained++; }
             }
             const bool two = kb + 1 < nkb;
             float2 v0[4], v1[4];
@@ -519,12 +568,15 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
                 }
             }
             mbar_wait(pl_empty(ps), pphase ^ 1);
-            split_store(smem + ps * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v0, pconj);
+            if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + ps * 32u, v0, pconj); }
+            else split_store(smem + ps * S::PL_STAGE, S::B_PLANE, prow, pkc, v0, pconj);
             if (two) {
                 mbar_wait(pl_empty(ps + 1), pphase ^ 1);
-                split_store(smem + (ps + 1) * S::PL_STAGE + plane_base, plane_bytes, prow, pkc, v1, pconj);
+                if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + (ps + 1) * 32u, v1, pconj); }
+                else split_store(smem + (ps + 1) * S::PL_STAGE, S::B_PLANE, prow, pkc, v1, pconj);
             }
-            fence_proxy_async_smem();
+            if (feeds_a) { tmem_st_wait(); tc_fence_before(); }
+            else fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(pl_full(ps));
@@ -575,34 +627,32 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             int ps = 0;
             uint32_t pphase = 0;
             for (uint32_t kb = 0; kb < nkb; kb++) {
-                const uint32_t c = kb / ACC_KCB, set = c & 1;
+                const uint32_t c = kb / ACC_KCB;
                 const bool first = (kb % ACC_KCB) == 0;
-                if (first && c >= 2) mbar_wait(accempty_bar(set), ((c >> 1) - 1) & 1);
+                if (first && c >= 1) mbar_wait(accempty_bar(0), (c - 1) & 1);
                 mbar_wait(pl_full(ps), pphase);
                 tc_fence_after();
-                const uint32_t d_re = tmem_base + set * 256u, d_im = d_re + 128u;
-                const uint32_t sa = smem_u32(smem + ps * S::PL_STAGE);
-                const uint32_t sb = sa + 4 * S::A_PLANE;
-                const uint64_t a_rh = make_smem_desc(sa), a_rl = make_smem_desc(sa + S::A_PLANE),
-                               a_ih = make_smem_desc(sa + 2 * S::A_PLANE), a_il = make_smem_desc(sa + 3 * S::A_PLANE);
+                const uint32_t d_re = tmem_base, d_im = d_re + 128u;
+                const uint32_t a_rh = tmem_base + ACC_APL_COL0 + ps * 32u, a_rl = a_rh + 8, a_ih = a_rh + 16, a_il = a_rh + 24;
+                const uint32_t sb = smem_u32(smem + ps * S::PL_STAGE);
                 const uint64_t b_rh = make_smem_desc(sb), b_rl = make_smem_desc(sb + S::B_PLANE),
                                b_ih = make_smem_desc(sb + 2 * S::B_PLANE), b_il = make_smem_desc(sb + 3 * S::B_PLANE);
                 const uint32_t acc = first ? 0u : 1u;
                 if (elect_one()) {
-                    umma_tf32(d_re, a_rh, b_rl, IDESC, acc);
-                    umma_tf32(d_re, a_rl, b_rh, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_il, IDESC_NEG, 1u);
-                    umma_tf32(d_re, a_il, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_re, a_rh, b_rh, IDESC, 1u);
-                    umma_tf32(d_re, a_ih, b_ih, IDESC_NEG, 1u);
-                    umma_tf32(d_im, a_rh, b_il, IDESC, acc);
-                    umma_tf32(d_im, a_rl, b_ih, IDESC, 1u);
-                    umma_tf32(d_im, a_ih, b_rl, IDESC, 1u);
-                    umma_tf32(d_im, a_il, b_rh, IDESC, 1u);
-                    umma_tf32(d_im, a_rh, b_ih, IDESC, 1u);
-                    umma_tf32(d_im, a_ih, b_rh, IDESC, 1u);
+                    umma_tf32_ts(d_re, a_rh, b_rl, IDESC, acc);
+                    umma_tf32_ts(d_re, a_rl, b_rh, IDESC, 1u);
+                    umma_tf32_ts(d_re, a_ih, b_il, IDESC_NEG, 1u);
+                    umma_tf32_ts(d_re, a_il, b_ih, IDESC_NEG, 1u);
+                    umma_tf32_ts(d_re, a_rh, b_rh, IDESC, 1u);
+                    umma_tf32_ts(d_re, a_ih, b_ih, IDESC_NEG, 1u);
+                    umma_tf32_ts(d_im, a_rh, b_il, IDESC, acc);
+                    umma_tf32_ts(d_im, a_rl, b_ih, IDESC, 1u);
+                    umma_tf32_ts(d_im, a_ih, b_rl, IDESC, 1u);
+                    umma_tf32_ts(d_im, a_il, b_rh, IDESC, 1u);
+                    umma_tf32_ts(d_im, a_rh, b_ih, IDESC, 1u);
+                    umma_tf32_ts(d_im, a_ih, b_rh, IDESC, 1u);
                     umma_commit(pl_empty(ps));
-                    if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(set));
+                    if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(0));
                 }
                 __syncwarp();
                 if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
@@ -693,7 +743,7 @@ constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
 constexpr int SK_APL_COLS = 4 * TC_BK;                     // TMEM columns of one A stage: planes rh | rl | ih | il, 8 k each
 constexpr int SK_BREP = 1;                      // streamed-B mode: replicas of the pre-split planes in global memory (CTA b reads
                                                 // replica b % SK_BREP, so that 148 SMs do not hammer the same 64 L2 lines at once)
-constexpr int SK_BST = 4;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
+constexpr int SK_BST = 8;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
 constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + 2 * SK_BST;
 constexpr int SK_BUDGET = 227 * 1024;
 
@@ -754,26 +804,6 @@ __device__ __forceinline__ void split_store_b(uint8_t* kb_base, int plane_bytes,
 // bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks stay
 // conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
 __device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, A operand in tensor memory (lane = row, one 32-bit column per k)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // BSTREAM: the small operand's planes do not fit in shared memory (N*K*16 > 64 KB): a tiny pre-pass
 // (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and lane 8 of the copy warp
