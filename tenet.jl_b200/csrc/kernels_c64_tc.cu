@@ -427,11 +427,10 @@ struct AccSmem {
     static constexpr int RAW_STAGE = 2 * RAW_HALF;                     // A then B
     static constexpr int RAW_OFF = ACC_PL_STAGES * PL_STAGE;
     static constexpr int BAR_OFF = RAW_OFF + ACC_RAW_STAGES * RAW_STAGE;
-    // raw_full[R], raw_empty[R], pl_full[P], pl_empty[P], accfull[2], accempty[2]
-    static constexpr int NBARS = 2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 4;
+    // raw_full[R], raw_empty[R], pl_full[P], pl_empty[P], accfull, accempty
+    static constexpr int NBARS = 2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 2;
     static constexpr int TMEM_OFF = BAR_OFF + NBARS * 8;
-    static constexpr int CN_OFF = (TMEM_OFF + 4 + 15) / 16 * 16;
-    static constexpr int TOTAL = CN_OFF + ACC_NT * 8;
+    static constexpr int TOTAL = TMEM_OFF + 16;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -451,26 +450,32 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t tilesM = (p.M + TC_BM - 1) / TC_BM, tilesN = (p.N + ACC_NT - 1) / ACC_NT;
     const uint32_t ntiles = tilesM * tilesN;
-    const uint32_t zsplit = blockIdx.x / ntiles;
-    uint32_t bm, bn;
-    raster(blockIdx.x - zsplit * ntiles, tilesM, tilesN, bm, bn);
-    const uint32_t m0 = bm * TC_BM, n0 = bn * ACC_NT;
-    const uint32_t mv = (p.M - m0) < TC_BM ? (p.M - m0) : TC_BM;      // valid rows / columns of a ragged edge tile
-    const uint32_t nv = (p.N - n0) < ACC_NT ? (p.N - n0) : ACC_NT;
+    const uint32_t nwork = ntiles * p.splitk;                         // persistent: CTA b takes work items b, b+grid, ...
     const uint32_t nkb_total = (p.K + TC_BK - 1) / TC_BK;
-    const uint32_t kb0 = zsplit * p.kb_per_split;
-    const uint32_t nkb = (nkb_total - kb0) < p.kb_per_split ? (nkb_total - kb0) : p.kb_per_split;
-    const uint32_t nchunks = (nkb + ACC_KCB - 1) / ACC_KCB;
+    // geometry of work item w (tile + K split): everything the three roles need, recomputed identically by each
+    struct Work { uint32_t m0, n0, mv, nv, kb0, nkb, nchunks, zsplit; };
+    auto work = [&](uint32_t w) {
+        Work t;
+        t.zsplit = w / ntiles;
+        uint32_t bm, bn;
+        raster(w - t.zsplit * ntiles, tilesM, tilesN, bm, bn);
+        t.m0 = bm * TC_BM; t.n0 = bn * ACC_NT;
+        t.mv = (p.M - t.m0) < TC_BM ? (p.M - t.m0) : TC_BM;           // valid rows / columns of a ragged edge tile
+        t.nv = (p.N - t.n0) < ACC_NT ? (p.N - t.n0) : ACC_NT;
+        t.kb0 = t.zsplit * p.kb_per_split;
+        t.nkb = (nkb_total - t.kb0) < p.kb_per_split ? (nkb_total - t.kb0) : p.kb_per_split;
+        t.nchunks = (t.nkb + ACC_KCB - 1) / ACC_KCB;
+        return t;
+    };
 
     const uint32_t bar0 = smem_u32(smem + S::BAR_OFF);
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (ACC_RAW_STAGES + s); };
     auto pl_full = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + s); };
     auto pl_empty = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + ACC_PL_STAGES + s); };
-    auto accfull_bar = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + s); };
-    auto accempty_bar = [&](int s) { return bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 2 + s); };
+    const uint32_t accfull_bar = bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES);
+    const uint32_t accempty_bar = accfull_bar + 8u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
-    int64_t* cn_tab = reinterpret_cast<int64_t*>(smem + S::CN_OFF);
 
     if (tid == 0) {
         for (int s = 0; s < ACC_RAW_STAGES; s++) {
@@ -481,15 +486,11 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             mbar_init(pl_full(s), ACC_WORKERS / 32);
             mbar_init(pl_empty(s), 1);                    // tcgen05.commit
         }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(accfull_bar(s), 1);
-            mbar_init(accempty_bar(s), ACC_WORKERS / 32);
-        }
+        mbar_init(accfull_bar, 1);
+        mbar_init(accempty_bar, ACC_WORKERS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
-    if (p.splitk == 1)
-        for (int i = tid; i < (int)nv; i += ACC_THREADS) cn_tab[i] = tabc(p.cn, n0 + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -506,13 +507,13 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         // A feeders: TMEM lane = row, columns of this thread's 4 k inside a stage: plane*8 + pkc*4
         const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + ACC_APL_COL0 + (uint32_t)(pkc * 4);
         const int raw_base = S::RAW_OFF + (feeds_a ? 0 : S::RAW_HALF) + (pkc * 4 * TC_BM + prow) * 8;
-        const bool row_ok = (uint32_t)prow < (feeds_a ? mv : nv);
         const int q = warp & 3, g = warp >> 2;        // TMEM lane quarter, 32-column group
+        const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
+        const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
         float tr[32], ti[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) { tr[j] = 0.f; ti[j] = 0.f; }
-        auto drain = [&](uint32_t c) {
-            mbar_wait(accfull_bar(0), c & 1);
+        uint32_t gdrained = 0;                         // chunks drained so far by this CTA (all work items)
+        auto drain = [&]() {
+            mbar_wait(accfull_bar, gdrained & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32);
 #pragma unroll
@@ -529,109 +530,123 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accempty_bar(0));
+            if (lane == 0) mbar_arrive(accempty_bar);
+            gdrained++;
         };
 
-        // Two k-blocks per iteration: one fence.proxy.async + one round of barrier traffic per 16 k, and twice the
-        // independent work in flight per warp (the loop is latency- not issue-bound).  Stage counts are even.
+        // Two k-blocks per iteration: one fence + one round of barrier traffic per 16 k, and twice the independent work
+        // in flight per warp (the loop is latency- not issue-bound).  Stage counts are even.
         static_assert(ACC_RAW_STAGES % 2 == 0 && ACC_PL_STAGES % 2 == 0 && ACC_KCB % 2 == 0, "pairs of k-blocks");
         int rs = 0, ps = 0;
-        uint32_t rphase = 0, pphase = 0, drained = 0;
-        for (uint32_t kb = 0; kb < nkb; kb += 2) {
-            // single accumulator set: chunk c-1 must be drained before the MMAs of chunk c start.  Do it once the plane
-            // ring is primed with the first stages of chunk c (they only need MMAs of chunk c-1 to retire), so the
-            // tensor core restarts on ready stages right after the drain.
-            if (kb >= ACC_KCB && kb % ACC_KCB == ACC_PL_STAGES) {
-                const uint32_t c = kb / ACC_KCB;
-                while (drained < c) { drain(drained); drained++; }
-            }
-            const bool two = kb + 1 < nkb;
-            float2 v0[4], v1[4];
-            mbar_wait(raw_full(rs), rphase);
-            {
-                const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
-                const uint32_t kleft = p.K - (kb0 + kb) * TC_BK;      // >= 8 except in the last k-block of a ragged K
+        uint32_t rphase = 0, pphase = 0;
+        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const Work t = work(w);
+            const bool row_ok = (uint32_t)prow < (feeds_a ? t.mv : t.nv);
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
-                    if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v0[i] = make_float2(0.f, 0.f);   // stale smem beyond the edge
+            for (int j = 0; j < 32; j++) { tr[j] = 0.f; ti[j] = 0.f; }
+            uint32_t drained = 0;                      // chunks of THIS work item drained
+            for (uint32_t kb = 0; kb < t.nkb; kb += 2) {
+                // single accumulator set: chunk c-1 must be drained before the MMAs of chunk c start.  Do it once the
+                // plane ring is primed with the first stages of chunk c (they only need MMAs of chunk c-1 to retire),
+                // so the tensor core restarts on ready stages right after the drain.
+                if (kb >= ACC_KCB && kb % ACC_KCB == ACC_PL_STAGES) {
+                    const uint32_t c = kb / ACC_KCB;
+                    while (drained < c) { drain(); drained++; }
                 }
-            }
-            if (two) {
-                mbar_wait(raw_full(rs + 1), rphase);
-                const uint8_t* raw = smem + (rs + 1) * S::RAW_STAGE + raw_base;
-                const uint32_t kleft = p.K - (kb0 + kb + 1) * TC_BK;
+                const bool two = kb + 1 < t.nkb;
+                float2 v0[4], v1[4];
+                mbar_wait(raw_full(rs), rphase);
+                {
+                    const uint8_t* raw = smem + rs * S::RAW_STAGE + raw_base;
+                    const uint32_t kleft = p.K - (t.kb0 + kb) * TC_BK;   // >= 8 except in the last k-block of a ragged K
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    v1[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
-                    if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v1[i] = make_float2(0.f, 0.f);
+                    for (int i = 0; i < 4; i++) {
+                        v0[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                        if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v0[i] = make_float2(0.f, 0.f);   // stale smem beyond the edge
+                    }
                 }
-            }
-            mbar_wait(pl_empty(ps), pphase ^ 1);
-            if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + ps * 32u, v0, pconj); }
-            else split_store(smem + ps * S::PL_STAGE, S::B_PLANE, prow, pkc, v0, pconj);
-            if (two) {
-                mbar_wait(pl_empty(ps + 1), pphase ^ 1);
-                if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + (ps + 1) * 32u, v1, pconj); }
-                else split_store(smem + (ps + 1) * S::PL_STAGE, S::B_PLANE, prow, pkc, v1, pconj);
-            }
-            if (feeds_a) { tmem_st_wait(); tc_fence_before(); }
-            else fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(pl_full(ps));
-                mbar_arrive(raw_empty(rs));
+                mbar_wait(raw_full(rs + 1), rphase);        // an odd tail k-block is a dummy stage on every role (phases stay aligned)
                 if (two) {
+                    const uint8_t* raw = smem + (rs + 1) * S::RAW_STAGE + raw_base;
+                    const uint32_t kleft = p.K - (t.kb0 + kb + 1) * TC_BK;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v1[i] = *reinterpret_cast<const float2*>(raw + i * TC_BM * 8);
+                        if (!row_ok || (uint32_t)(pkc * 4 + i) >= kleft) v1[i] = make_float2(0.f, 0.f);
+                    }
+                }
+                mbar_wait(pl_empty(ps), pphase ^ 1);
+                if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + ps * 32u, v0, pconj); }
+                else split_store(smem + ps * S::PL_STAGE, S::B_PLANE, prow, pkc, v0, pconj);
+                mbar_wait(pl_empty(ps + 1), pphase ^ 1);
+                if (two) {
+                    if (feeds_a) { tc_fence_after(); split_store_tmem(a_lane + (ps + 1) * 32u, v1, pconj); }
+                    else split_store(smem + (ps + 1) * S::PL_STAGE, S::B_PLANE, prow, pkc, v1, pconj);
+                }
+                if (feeds_a) { tmem_st_wait(); tc_fence_before(); }
+                else fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(pl_full(ps));
+                    mbar_arrive(raw_empty(rs));
                     mbar_arrive(pl_full(ps + 1));
                     mbar_arrive(raw_empty(rs + 1));
                 }
+                rs += 2; if (rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
+                ps += 2; if (ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
             }
-            rs += 2; if (rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
-            ps += 2; if (ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
-        }
-        while (drained < nchunks) { drain(drained); drained++; }
+            while (drained < t.nchunks) { drain(); drained++; }
 
-        // ---- epilogue: totals -> alpha/beta -> scatter ----
-        const uint32_t row = q * 32 + lane;
-        if (row < mv) {
-            if (p.splitk == 1) {
-                float2* __restrict__ Crow = p.C + tabc(p.cm, m0 + row);
-                const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
-                const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
+            // ---- epilogue: totals -> alpha/beta -> scatter (the copy warp is already fetching the next work item) ----
+            const uint32_t row = q * 32 + lane;
+            if (row < t.mv) {
+                if (p.splitk == 1) {
+                    float2* __restrict__ Crow = p.C + tabc(p.cm, t.m0 + row);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if ((uint32_t)(g * 32 + j) >= nv) break;
-                    float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
-                    float2* dst = Crow + cn_tab[g * 32 + j];
-                    if (has_beta) {
-                        float2 old = *dst;
-                        o.x += br * old.x - bi * old.y;
-                        o.y += br * old.y + bi * old.x;
+                    for (int j = 0; j < 32; j++) {
+                        if ((uint32_t)(g * 32 + j) >= t.nv) break;
+                        float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
+                        float2* dst = Crow + tabc(p.cn, t.n0 + g * 32 + j);
+                        if (has_beta) {
+                            float2 old = *dst;
+                            o.x += br * old.x - bi * old.y;
+                            o.y += br * old.y + bi * old.x;
+                        }
+                        *dst = o;
                     }
-                    *dst = o;
-                }
-            } else {
-                float2* __restrict__ W = p.ws + ((uint64_t)zsplit * p.N + n0) * p.M + (m0 + row);
+                } else {
+                    float2* __restrict__ W = p.ws + ((uint64_t)t.zsplit * p.N + t.n0) * p.M + (t.m0 + row);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if ((uint32_t)(g * 32 + j) >= nv) break;
-                    W[(uint64_t)(g * 32 + j) * p.M] = make_float2(tr[j], ti[j]);
+                    for (int j = 0; j < 32; j++) {
+                        if ((uint32_t)(g * 32 + j) >= t.nv) break;
+                        W[(uint64_t)(g * 32 + j) * p.M] = make_float2(tr[j], ti[j]);
+                    }
                 }
             }
         }
     } else if (warp == 16) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ---- MMA issuer: warp-uniform loop, one elected lane issues (see elect_one) ----
-        {
-            constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
-            int ps = 0;
-            uint32_t pphase = 0;
-            for (uint32_t kb = 0; kb < nkb; kb++) {
-                const uint32_t c = kb / ACC_KCB;
+        constexpr uint32_t IDESC = make_idesc<ACC_NT>(false), IDESC_NEG = make_idesc<ACC_NT>(true);
+        int ps = 0;
+        uint32_t pphase = 0, gchunk = 0;               // chunks started so far by this CTA
+        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const Work t = work(w);
+            const uint32_t nkb2 = (t.nkb + 1) & ~1u;      // odd tail: one dummy stage (no MMAs), see the workers
+            for (uint32_t kb = 0; kb < nkb2; kb++) {
                 const bool first = (kb % ACC_KCB) == 0;
-                if (first && c >= 1) mbar_wait(accempty_bar(0), (c - 1) & 1);
+                if (first && kb < t.nkb) {
+                    if (gchunk >= 1) mbar_wait(accempty_bar, (gchunk - 1) & 1);
+                    gchunk++;
+                }
                 mbar_wait(pl_full(ps), pphase);
                 tc_fence_after();
+                if (kb >= t.nkb) {
+                    if (elect_one()) umma_commit(pl_empty(ps));
+                    __syncwarp();
+                    if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
+                    continue;
+                }
                 const uint32_t d_re = tmem_base, d_im = d_re + 128u;
                 const uint32_t a_rh = tmem_base + ACC_APL_COL0 + ps * 32u, a_rl = a_rh + 8, a_ih = a_rh + 16, a_il = a_rh + 24;
                 const uint32_t sb = smem_u32(smem + ps * S::PL_STAGE);
@@ -652,7 +667,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
                     umma_tf32_ts(d_im, a_rh, b_ih, IDESC, 1u);
                     umma_tf32_ts(d_im, a_ih, b_rh, IDESC, 1u);
                     umma_commit(pl_empty(ps));
-                    if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == nkb - 1) umma_commit(accfull_bar(0));
+                    if ((kb % ACC_KCB) == ACC_KCB - 1 || kb == t.nkb - 1) umma_commit(accfull_bar);
                 }
                 __syncwarp();
                 if (++ps == ACC_PL_STAGES) { ps = 0; pphase ^= 1; }
@@ -663,25 +678,30 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // idle warps: only there to complete warpgroup 4
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B ----
+        // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B; it runs ahead of
+        // the workers into the next work item by the depth of the raw ring ----
         int rs = 0;
         uint32_t rphase = 0;
         const bool is_a = lane < 8;
         const int krow = lane & 7;
-        const float2* src = is_a ? p.A + m0 : p.B + n0;
         const int64_t ld = is_a ? p.lda : p.ldb;
-        const uint32_t row_bytes = (is_a ? mv : nv) * 8;          // multiple of 16: M, N even (eligibility)
-        for (uint32_t kb = 0; kb < nkb; kb++) {
-            const uint32_t k0 = (kb0 + kb) * TC_BK;
-            const uint32_t kv = (p.K - k0) < TC_BK ? (p.K - k0) : TC_BK;
-            mbar_wait(raw_empty(rs), rphase ^ 1);
-            if (lane == 0) mbar_expect_tx(raw_full(rs), kv * (mv + nv) * 8);
-            __syncwarp();
-            if (lane < 16 && (uint32_t)krow < kv) {
-                const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (is_a ? 0 : S::RAW_HALF) + krow * TC_BM * 8);
-                bulk_g2s(dst, src + (int64_t)(k0 + krow) * ld, row_bytes, raw_full(rs));
+        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const Work t = work(w);
+            const float2* src = is_a ? p.A + t.m0 : p.B + t.n0;
+            const uint32_t row_bytes = (is_a ? t.mv : t.nv) * 8;      // multiple of 16: M, N even (eligibility)
+            const uint32_t nkb2 = (t.nkb + 1) & ~1u;      // odd tail: one dummy stage (zero bytes)
+            for (uint32_t kb = 0; kb < nkb2; kb++) {
+                const uint32_t k0 = (t.kb0 + kb) * TC_BK;
+                const uint32_t kv = kb >= t.nkb ? 0u : ((p.K - k0) < TC_BK ? (p.K - k0) : TC_BK);
+                mbar_wait(raw_empty(rs), rphase ^ 1);
+                if (lane == 0) mbar_expect_tx(raw_full(rs), kv * (t.mv + t.nv) * 8);
+                __syncwarp();
+                if (lane < 16 && (uint32_t)krow < kv) {
+                    const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (is_a ? 0 : S::RAW_HALF) + krow * TC_BM * 8);
+                    bulk_g2s(dst, src + (int64_t)(k0 + krow) * ld, row_bytes, raw_full(rs));
+                }
+                if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
             }
-            if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
         }
     }
     tc_fence_before();
@@ -698,7 +718,8 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
         TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AccSmem::TOTAL));
         configured[ctx->device & 15] = true;
     }
-    const unsigned grid = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + ACC_NT - 1) / ACC_NT) * a.splitk;
+    unsigned grid = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + ACC_NT - 1) / ACC_NT) * a.splitk;
+    if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;   // persistent: one CTA per SM walks the work items
     c64_tf32x3_acc_kernel<<<grid, ACC_THREADS, AccSmem::TOTAL, ctx->stream>>>(a);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());

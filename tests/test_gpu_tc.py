@@ -14,7 +14,8 @@ def crand(rng, shape, dt=np.complex64):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 40), (128, 128, 16), (384, 512, 200), (512, 512, 1024),
                                    (256, 1024, 8192),
-                                   (200, 130, 77), (1000, 34, 300), (64, 4096, 16384), (130, 258, 2050)])  # ragged / split-K
+                                   (200, 130, 77), (1000, 34, 300), (64, 4096, 16384), (130, 258, 2050),   # ragged / split-K
+                                   (2560, 1280, 40), (2500, 1300, 72), (4096, 1024, 264)])  # > 148 tiles: persistent CTAs, odd k-block counts
 def test_tc_matches_oracle(ctx, M, N, K):
     import tenet_jl_b200 as tb
     rng = np.random.default_rng(M + N + K)
