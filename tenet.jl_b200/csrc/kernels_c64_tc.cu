@@ -18,6 +18,7 @@
 //                              round-to-nearest FP32 totals, ragged edges, split-K
 //   c64_tf32x3_stem_kernel<NT> persistent HBM-bound kernel for huge x small steps (small operand resident as planes,
 //                              sorted-pattern coalesced epilogue overlapped with the next tile)
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <stdint.h>
@@ -443,7 +444,44 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const TcArgs p) {
+// 2-D TMA tile load (UTMALDG): box {128 elements of 8 B along the free index, 8 k-rows} of an operand stored [K][M]
+// with an arbitrary leading dimension, ONE request per operand and k-block instead of eight 1 KB bulk copies (the
+// per-request service time of the copy engine, not bytes, was what starved the GEMM kernel's raw ring).  Rows / k
+// beyond the tensor's extent are zero-filled by the hardware, which also covers ragged edge tiles.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, uint32_t c0, uint32_t c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst_smem), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// host: tensor map over a dense-rows operand  X[k][m] = base[m + ld*k]  (8-byte elements), box = 128 x 8
+typedef CUresult (*tnb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tnb_encode_tiled_fn get_encode_tiled() {
+    static tnb_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (tnb_encode_tiled_fn)f;
+    }
+    return fn;
+}
+static bool make_operand_map(CUtensorMap* tm, const float2* base, uint64_t rows, uint64_t K, int64_t ld) {
+    tnb_encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {rows, K};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};                // bytes between consecutive k (multiple of 16)
+    const cuuint32_t box[2] = {TC_BM, TC_BK};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const TcArgs p, const __grid_constant__ CUtensorMap tmA,
+                                                                        const __grid_constant__ CUtensorMap tmB) {
     using S = AccSmem;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -678,27 +716,21 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");   // idle warps: only there to complete warpgroup 4
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        // ---- bulk-copy issuer (warp 17): lanes 0-7 fetch the 8 k-rows of A, lanes 8-15 those of B; it runs ahead of
-        // the workers into the next work item by the depth of the raw ring ----
+        // ---- copy issuer (warp 17): one 2-D TMA tile load per operand and k-block (lane 0: A, lane 1: B); it runs ahead
+        // of the workers into the next work item by the depth of the raw ring ----
         int rs = 0;
         uint32_t rphase = 0;
-        const bool is_a = lane < 8;
-        const int krow = lane & 7;
-        const int64_t ld = is_a ? p.lda : p.ldb;
         for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
             const Work t = work(w);
-            const float2* src = is_a ? p.A + t.m0 : p.B + t.n0;
-            const uint32_t row_bytes = (is_a ? t.mv : t.nv) * 8;      // multiple of 16: M, N even (eligibility)
             const uint32_t nkb2 = (t.nkb + 1) & ~1u;      // odd tail: one dummy stage (zero bytes)
             for (uint32_t kb = 0; kb < nkb2; kb++) {
                 const uint32_t k0 = (t.kb0 + kb) * TC_BK;
-                const uint32_t kv = kb >= t.nkb ? 0u : ((p.K - k0) < TC_BK ? (p.K - k0) : TC_BK);
                 mbar_wait(raw_empty(rs), rphase ^ 1);
-                if (lane == 0) mbar_expect_tx(raw_full(rs), kv * (t.mv + t.nv) * 8);
+                if (lane == 0) mbar_expect_tx(raw_full(rs), kb < t.nkb ? (uint32_t)S::RAW_STAGE : 0u);   // full boxes: OOB is zero-filled
                 __syncwarp();
-                if (lane < 16 && (uint32_t)krow < kv) {
-                    const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (is_a ? 0 : S::RAW_HALF) + krow * TC_BM * 8);
-                    bulk_g2s(dst, src + (int64_t)(k0 + krow) * ld, row_bytes, raw_full(rs));
+                if (kb < t.nkb && lane < 2) {
+                    const uint32_t dst = smem_u32(smem + S::RAW_OFF + rs * S::RAW_STAGE + (lane == 0 ? 0 : S::RAW_HALF));
+                    tma_load_2d(dst, lane == 0 ? &tmA : &tmB, lane == 0 ? t.m0 : t.n0, k0, raw_full(rs));
                 }
                 if (++rs == ACC_RAW_STAGES) { rs = 0; rphase ^= 1; }
             }
@@ -720,7 +752,11 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
     }
     unsigned grid = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + ACC_NT - 1) / ACC_NT) * a.splitk;
     if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;   // persistent: one CTA per SM walks the work items
-    c64_tf32x3_acc_kernel<<<grid, ACC_THREADS, AccSmem::TOTAL, ctx->stream>>>(a);
+    CUtensorMap tmA, tmB;
+    if (!make_operand_map(&tmA, a.A, a.M, a.K, a.lda) || !make_operand_map(&tmB, a.B, a.N, a.K, a.ldb))
+        return tnb_set_error(ctx, TNB_ECUDA, "cuTensorMapEncodeTiled failed (M=%u N=%u K=%u lda=%lld ldb=%lld)", a.M, a.N, a.K,
+                             (long long)a.lda, (long long)a.ldb);
+    c64_tf32x3_acc_kernel<<<grid, ACC_THREADS, AccSmem::TOTAL, ctx->stream>>>(a, tmA, tmB);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
