@@ -866,7 +866,7 @@ __device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 
 // (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and lane 8 of the copy warp
 // streams one 2*B_KB stage per k-block (one bulk copy, L2-resident source) next to the A rows.
 template <int NT, bool BSTREAM>   // NT: columns of the small operand per launch, padded (16, 32, 64)
-__global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p) {
+__global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p, const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nkb = (uint32_t)p.K / TC_BK;
@@ -1156,19 +1156,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             }
         }
     } else {
-        // ---- bulk-copy issuer: lanes 0-7 fetch the 8 k-rows (1 KB each) of the A tile; lane 8 streams the B planes.
+        // ---- copy issuer: lane 0 fetches the A tile of every k-block with one 2-D TMA load; lane 8 streams the B planes.
         // The two loops are INDEPENDENT (divergent on purpose): the A ring runs ahead by its full depth. ----
-        if (lane < 8) {
+        if (lane == 0) {
+            // one 2-D TMA tile load (128 rows x 8 k) per k-block
             int rs = 0;
             uint32_t rphase = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                const float2* src = p.A + t * TC_BM;
                 for (uint32_t kb = 0; kb < nkb; kb++) {
                     mbar_wait(raw_empty(rs), rphase ^ 1);
-                    if (lane == 0) mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
-                    __syncwarp(0xffu);
-                    const uint32_t dst = smem_u32(smem + p.off_raw + rs * SK_RAW_STAGE + lane * TC_BM * 8);
-                    bulk_g2s(dst, src + (int64_t)(kb * TC_BK + lane) * p.lda, TC_BM * 8, raw_full(rs));
+                    mbar_expect_tx(raw_full(rs), SK_RAW_STAGE);
+                    tma_load_2d(smem_u32(smem + p.off_raw + rs * SK_RAW_STAGE), &tmA, (uint32_t)(t * TC_BM), kb * TC_BK, raw_full(rs));
                     if (++rs == SK_RAW) { rs = 0; rphase ^= 1; }
                 }
             }
@@ -1219,7 +1217,10 @@ int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
-    c64_tf32x3_stem_kernel<NT, BSTREAM><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a);
+    CUtensorMap tmA;
+    if (!make_operand_map(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, a.lda))
+        return tnb_set_error(ctx, TNB_ECUDA, "cuTensorMapEncodeTiled failed (M=%lld K=%d lda=%lld)", (long long)a.M, a.K, (long long)a.lda);
+    c64_tf32x3_stem_kernel<NT, BSTREAM><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a, tmA);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
