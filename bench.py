@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (description, dtype)
     "sycamore53_m14": "Sycamore-like 53-qubit depth-14 random-circuit amplitude, complex64, sliced (BASELINE configs[2])",
+    "sycamore53_m14_v1": "same network, earlier committed path (flops objective: 4096 slices x 2^37.95 MACs, HBM-bound stem steps dominate)",
     "sycamore53_m14_greedy": "same network, round-1 first-light path (plain greedy, 2^63 MACs total): two 16384x8192x8192 GEMMs dominate",
     "sycamore53_m10": "Sycamore-like 53-qubit depth-10 random-circuit amplitude, complex64, sliced",
     "regular3_n60_d4": "random 3-regular network, 60 tensors, bond 4, complex64 (BASELINE configs[1] scaled to fit)",
@@ -47,7 +48,7 @@ def build_workload(tb, name, path_file=""):
     if name == "peps6x6_d4_boundary":
         tn, _ = tb.workloads.peps_norm_network(6, 6, D=4, p=2, dtype=np.complex128, seed=4)
         return tn, tb.workloads.peps_boundary_path(6, 6)
-    if name in ("sycamore53_m14", "sycamore53_m14_greedy", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
+    if name in ("sycamore53_m14", "sycamore53_m14_v1", "sycamore53_m14_greedy", "sycamore53_m10", "regular3_n60_d4", "regular3_n100_d4", "peps6x6_d4"):
         tn = network(name)
         fn = path_file or os.path.join(ROOT, "bench_paths", name + ".json")
         if not os.path.exists(fn):
@@ -110,7 +111,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(tb, tn, path, budget_macs_log2=39.5):
+def cpu_sample(tb, tn, path, budget_macs_log2=38.5):
     """A bounded CPU sample of the same workload: slice further until one sub-slice is ~2^budget MACs, then time
     the oracle on sub-slice 0.  Returns (flops, seconds, description)."""
     from oracle import einsum_oracle as orc

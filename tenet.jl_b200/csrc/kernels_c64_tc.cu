@@ -431,7 +431,8 @@ struct AccSmem {
     // raw_full[R], raw_empty[R], pl_full[P], pl_empty[P], accfull, accempty
     static constexpr int NBARS = 2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES + 2;
     static constexpr int TMEM_OFF = BAR_OFF + NBARS * 8;
-    static constexpr int TOTAL = TMEM_OFF + 16;
+    static constexpr int CN_OFF = (TMEM_OFF + 4 + 15) / 16 * 16;       // column offsets of the current / next work item
+    static constexpr int TOTAL = CN_OFF + 2 * ACC_NT * 8;
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
     const uint32_t accfull_bar = bar0 + 8u * (2 * ACC_RAW_STAGES + 2 * ACC_PL_STAGES);
     const uint32_t accempty_bar = accfull_bar + 8u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::TMEM_OFF);
+    int64_t* cn_tab = reinterpret_cast<int64_t*>(smem + S::CN_OFF);
 
     if (tid == 0) {
         for (int s = 0; s < ACC_RAW_STAGES; s++) {
@@ -577,9 +579,17 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
         static_assert(ACC_RAW_STAGES % 2 == 0 && ACC_PL_STAGES % 2 == 0 && ACC_KCB % 2 == 0, "pairs of k-blocks");
         int rs = 0, ps = 0;
         uint32_t rphase = 0, pphase = 0;
-        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        uint32_t item = 0;
+        for (uint32_t w = blockIdx.x; w < nwork; w += gridDim.x, item++) {
             const Work t = work(w);
             const bool row_ok = (uint32_t)prow < (feeds_a ? t.mv : t.nv);
+            // output column offsets of this work item -> shared (double buffered: the slowest warp may still be in the
+            // previous item's epilogue); one worker-only barrier per item, long before the epilogue needs the table
+            int64_t* cn_cur = cn_tab + (item & 1) * ACC_NT;
+            if (p.splitk == 1) {
+                if (tid < (int)t.nv) cn_cur[tid] = tabc(p.cn, t.n0 + tid);
+                asm volatile("bar.sync 2, 512;" ::: "memory");
+            }
 #pragma unroll
             for (int j = 0; j < 32; j++) { tr[j] = 0.f; ti[j] = 0.f; }
             uint32_t drained = 0;                      // chunks of THIS work item drained
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) c64_tf32x3_acc_kernel(const Tc
                     for (int j = 0; j < 32; j++) {
                         if ((uint32_t)(g * 32 + j) >= t.nv) break;
                         float2 o = make_float2(ar * tr[j] - ai * ti[j], ar * ti[j] + ai * tr[j]);
-                        float2* dst = Crow + tabc(p.cn, t.n0 + g * 32 + j);
+                        float2* dst = Crow + cn_cur[g * 32 + j];
                         if (has_beta) {
                             float2 old = *dst;
                             o.x += br * old.x - bi * old.y;

@@ -373,7 +373,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
 }
 
-template <typename E>   // float2 / double2
+template <typename E, int TM>   // float2 / double2; TM x 4 micro-tile of C per thread (TM = 2 or 4)
 __global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArgs p) {
     extern __shared__ __align__(16) unsigned char kred_smem[];
     constexpr int VEC = 16 / (int)sizeof(E);                       // elements per 16-byte copy
@@ -402,10 +402,10 @@ __global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArg
     const int per = p.mt * p.nt;
     const bool active = tid < p.kslices * per;
     const int ks = tid / per, r = tid - ks * per;
-    const int m0 = (r / p.nt) * 2, n0 = (r % p.nt) * 4;
-    E acc[2][4];
+    const int m0 = (r / p.nt) * TM, n0 = (r % p.nt) * 4;
+    E acc[TM][4];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < TM; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = ezero((E*)0);
 
@@ -419,17 +419,21 @@ __global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArg
             const E* sB = sA + tileA;
 #pragma unroll 4
             for (int kk = ks; kk < KS; kk += p.kslices) {
-                E a[2], b[4];
-                a[0] = sA[kk * M + m0]; a[1] = sA[kk * M + m0 + 1];
+                E a[TM], b[4];
+#pragma unroll
+                for (int i = 0; i < TM; i++) a[i] = sA[kk * M + m0 + i];
 #pragma unroll
                 for (int j = 0; j < 4; j++) b[j] = sB[kk * N + n0 + j];
-                if (p.conjA) { a[0] = econj(a[0]); a[1] = econj(a[1]); }
+                if (p.conjA) {
+#pragma unroll
+                    for (int i = 0; i < TM; i++) a[i] = econj(a[i]);
+                }
                 if (p.conjB) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) b[j] = econj(b[j]);
                 }
 #pragma unroll
-                for (int i = 0; i < 2; i++)
+                for (int i = 0; i < TM; i++)
 #pragma unroll
                     for (int j = 0; j < 4; j++) emac(acc[i][j], a[i], b[j]);
             }
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArg
     E* red = sm;
     if (active) {
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+        for (int i = 0; i < TM; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) red[(size_t)ks * M * N + (n0 + j) * M + m0 + i] = acc[i][j];
     }
@@ -574,7 +578,8 @@ int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
     KredArgs k;
     k.A = a.A; k.B = a.B; k.ws = a.ws; k.K = a.K; k.kchunk = a.kchunk;
     k.M = (int32_t)a.M; k.N = (int32_t)a.N; k.conjA = a.conjA; k.conjB = a.conjB;
-    k.mt = k.M / 2; k.nt = k.N / 4;
+    const int TM = (k.M % 4 == 0 && k.M * k.N >= 256) ? 4 : 2;     // 4 x 4 micro-tiles halve the shared-memory reads per MAC
+    k.mt = k.M / TM; k.nt = k.N / 4;
     int ks = 1;
     while (ks * 2 * k.mt * k.nt <= KRED_THREADS) ks *= 2;
     k.kslices = ks;
@@ -585,13 +590,14 @@ int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
     size_t smem = 2 * (size_t)KS * (k.M + k.N) * esz;
     const size_t red = (size_t)ks * k.M * k.N * esz;
     if (red > smem) smem = red;
-    if (dtype == TNB_C64) {
-        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_kred_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        einsum_kred_kernel<float2><<<(unsigned)a.splitk, KRED_THREADS, smem, ctx->stream>>>(k);
-    } else {
-        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_kred_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        einsum_kred_kernel<double2><<<(unsigned)a.splitk, KRED_THREADS, smem, ctx->stream>>>(k);
-    }
+#define TNB_KRED_LAUNCH(E, T)                                                                                              \
+    do {                                                                                                                   \
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_kred_kernel<E, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+        einsum_kred_kernel<E, T><<<(unsigned)a.splitk, KRED_THREADS, smem, ctx->stream>>>(k);                              \
+    } while (0)
+    if (dtype == TNB_C64) { if (TM == 4) TNB_KRED_LAUNCH(float2, 4); else TNB_KRED_LAUNCH(float2, 2); }
+    else { if (TM == 4) TNB_KRED_LAUNCH(double2, 4); else TNB_KRED_LAUNCH(double2, 2); }
+#undef TNB_KRED_LAUNCH
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;

@@ -17,7 +17,7 @@ import tenet_jl_b200 as tb  # noqa: E402
 
 
 def network(name):
-    if name in ("sycamore53_m14", "sycamore53_m14_greedy"):
+    if name in ("sycamore53_m14", "sycamore53_m14_v1", "sycamore53_m14_greedy"):
         tn, _ = tb.workloads.sycamore_amplitude_network(rows=9, cols=6, cycles=14, seed=53, dtype=np.complex64)
         return tn
     if name == "sycamore53_m10":
