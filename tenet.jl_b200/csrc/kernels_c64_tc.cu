@@ -8,16 +8,18 @@
 // Complex product from real sub-GEMMs:  Cre = Are.Bre - Aim.Bim,  Cim = Are.Bim + Aim.Bre  (minus sign = a_negate bit).
 // Each real product a*b is evaluated as  a_hi*b_lo + a_lo*b_hi + a_hi*b_hi  with x_hi = x & 0xffffe000 (what the
 // tensor core reads anyway), x_lo = x - x_hi (exact): 12 tcgen05.mma.kind::tf32 per 8 complex k per tile, FP32
-// accumulation in TMEM.  Operands are staged raw by cp.async.bulk, split into four planes per operand (re_hi, re_lo,
-// im_hi, im_lo) in the UMMA K-major no-swizzle core-matrix layout by worker warps; the permuted / split operand never
-// exists in global memory.
+// accumulation in TMEM.  Raw operand tiles arrive by 2-D TMA tile loads (a tensor map over the operand's own
+// leading dimension) and are split by worker warps into four planes per operand (re_hi, re_lo, im_hi, im_lo): the A
+// planes go to TENSOR MEMORY (tcgen05.st, ".ts" MMAs), the B planes to shared memory in the UMMA K-major no-swizzle
+// core-matrix layout; the permuted / split operand never exists in global memory.
 //
 // Three kernels share these pieces:
-//   c64_tf32x3_kernel<NT>      "fast mode": 128 x NT tile, whole K chained in TMEM (error grows with K), register prefetch
-//   c64_tf32x3_acc_kernel      default GEMM kernel: 128 x 128 tile, bulk-copy raw ring, TMEM chunks of 64 k drained into
-//                              round-to-nearest FP32 totals, ragged edges, split-K
-//   c64_tf32x3_stem_kernel<NT> persistent HBM-bound kernel for huge x small steps (small operand resident as planes,
-//                              sorted-pattern coalesced epilogue overlapped with the next tile)
+//   c64_tf32x3_kernel<NT>      "fast mode": 128 x NT tile, whole K chained in TMEM (error grows with K), register prefetch,
+//                              both operands in shared memory
+//   c64_tf32x3_acc_kernel      default GEMM kernel: persistent CTAs over 128 x 128 tiles, TMA raw ring, A in TMEM, TMEM chunks
+//                              of 128 k drained into round-to-nearest FP32 totals, ragged edges, split-K
+//   c64_tf32x3_stem_kernel     persistent kernel for huge x small steps (small operand resident as planes or streamed,
+//                              A in TMEM, sorted-pattern coalesced epilogue overlapped with the next tile)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdlib>
