@@ -162,3 +162,47 @@ def test_pathfinder_costs_and_slicing():
     assert len(bp.steps) == len(t53.tensors) - 1 and len(set(bp.sliced)) == len(bp.sliced)
     m3, x3, _ = orc.path_flops([t.inds for t in t53.tensors], t53.sizes(), bp.steps, sliced=bp.sliced)
     assert abs(np.log2(float(m3)) - bp.log2_macs) < 1e-6 and abs(np.log2(float(x3)) - bp.log2_max_size) < 1e-6
+
+
+def test_committed_path_kernel_selection(built_lib):
+    """dry plan of the committed 53-qubit path: the planner must route the work to the kernels bench.py reports on
+    (no silent fall-back of a big step to the generic kernel), with the workspace the streamed-B / split-K steps need."""
+    import tenet_jl_b200 as tb
+    from tools.make_paths import network
+    tn = network("sycamore53_m14")
+    path = tb.pathfinder.load_path(tn.inds("all"), os.path.join(ROOT, "bench_paths", "sycamore53_m14.json"))
+    plan = tb.ContractionPlan(tn, path, dry=True)
+    info = plan.info
+    assert info["nslices"] == 256 and info["nsteps_per_slice"] + info["nsteps_hoisted"] == len(tn.tensors) - 1
+    flops = {}
+    for s in range(plan.nsteps):
+        si = plan.step_info(s)
+        if not si["hoisted"]:
+            flops[si["kernel_name"]] = flops.get(si["kernel_name"], 0.0) + si["flops"]
+    tot = sum(flops.values())
+    assert abs(tot - info["flops_per_slice"]) / tot < 1e-9
+    tc = flops.get("c64_tf32x3", 0) + flops.get("stem_tc", 0)
+    assert tc / tot > 0.98, flops                              # tensor-core kernels carry the flops
+    assert flops.get("generic", 0) + flops.get("splitk", 0) < 1e-3 * tot, flops
+    assert "stream" in flops                                   # the environment-closing k-reduction step
+    assert info["workspace_bytes"] < 64 * 2 ** 30              # arena + workspace fit one B200 with room to spare
+
+
+def test_stem_plan_flags(built_lib):
+    """stem steps: power-of-two extents give a separable rank (bit deposit) and even run bases; an interleaved output
+    layout must still be recognised as a stem step with runs of the expected length."""
+    import tenet_jl_b200 as tb
+    a = np.zeros((2,) * 17 + (32,), np.complex64)
+    b = np.zeros((32, 32), np.complex64)
+    big = [f"m{i}" for i in range(17)]
+    for out, kern in [(None, "stem_tc"), (big[:3] + ["n"] + big[3:], "stem_tc"), (big[9:] + ["n"] + big[:9], "stem_tc")]:
+        tn = tb.TensorNetwork([tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"])])
+        plan = tb.ContractionPlan(tn, tb.ContractionPath([(0, 1)]), output=out, dry=True)
+        si = plan.step_info(0)
+        assert si["kernel_name"] == kern and si["M"] * si["N"] == (1 << 17) * 32 and si["K"] == 32
+    # small operand too large to stay resident: still the stem kernel (streamed-B mode)
+    b2 = np.zeros((128, 128), np.complex64)
+    a2 = np.zeros((2,) * 17 + (128,), np.complex64)
+    tn = tb.TensorNetwork([tb.Tensor(a2, big + ["k"]), tb.Tensor(b2, ["n", "k"])])
+    plan = tb.ContractionPlan(tn, tb.ContractionPath([(0, 1)]), dry=True)
+    assert plan.step_info(0)["kernel_name"] == "stem_tc"
