@@ -111,10 +111,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(tb, tn, path, budget_macs_log2=38.5):
-    """A bounded CPU sample of the same workload: slice further until one sub-slice is ~2^budget MACs, then time
-    the oracle on sub-slice 0.  Returns (flops, seconds, description)."""
-    from oracle import einsum_oracle as orc
+def subslice_path(tb, tn, path, budget_macs_log2=38.5):
+    """The committed path with extra sliced indices, added until one sub-slice costs <= 2^budget MACs: the piece of
+    the full-size workload a CPU can finish (also used by tests/test_gpu_zz_fullsize.py as the oracle-sized case)."""
     inputs = [t.inds for t in tn.tensors]
     sizes = tn.sizes()
     p = path
@@ -122,6 +121,15 @@ def cpu_sample(tb, tn, path, budget_macs_log2=38.5):
     while p.log2_macs > budget_macs_log2 and target > 8:
         target -= 1.0
         p = tb.find_slices(inputs, sizes, (), tb.ContractionPath(list(path.steps), tuple(p.sliced)), target)
+    return p
+
+
+def cpu_sample(tb, tn, path, budget_macs_log2=38.5):
+    """A bounded CPU sample of the same workload: slice further until one sub-slice is ~2^budget MACs, then time
+    the oracle on sub-slice 0.  Returns (flops, seconds, description)."""
+    from oracle import einsum_oracle as orc
+    inputs = [t.inds for t in tn.tensors]
+    p = subslice_path(tb, tn, path, budget_macs_log2)
     arrays = [t.parent for t in tn.tensors]
     sl = list(p.sliced)
     t0 = time.perf_counter()

@@ -317,15 +317,15 @@ def product_mps(bits: str, chi: int = 1, seed: int = 0, dtype=np.complex128) -> 
     Gprev_inv = np.eye(1)
     for i, ch in enumerate(bits):
         cl, cr = dims[i], dims[i + 1]
-        a = np.zeros((cl, 2, cr), dtype=np.complex128)
-        a[0, :, 0] = table[ch]
         if cr > 1:
             G = rng.standard_normal((cr, cr)) + 1j * rng.standard_normal((cr, cr))
-            G = G / np.linalg.norm(G, 2) + np.eye(cr)
+            # ||G||_2 of a complex Ginibre matrix with E|g|^2 = 2 is ~ 2 sqrt(2 cr): G/that + 1 is well conditioned
+            G = G / (2.0 * math.sqrt(2.0 * cr)) + np.eye(cr)
             Ginv = np.linalg.inv(G)
         else:
             G, Ginv = np.eye(1), np.eye(1)
-        a = np.einsum("ab,bpc,cd->apd", Gprev_inv, a, G)
+        # the un-gauged site is e_0 (x) |ch> (x) e_0^T, so G_prev^-1 . site . G is an outer product
+        a = Gprev_inv[:, 0][:, None, None] * np.asarray(table[ch])[None, :, None] * G[0, :][None, None, :]
         Gprev_inv = Ginv
         arrays.append(a.astype(dtype))
     arrays[0] = arrays[0].reshape(2, -1)
