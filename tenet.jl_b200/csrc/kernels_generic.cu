@@ -8,6 +8,7 @@
 // always-correct path (any rank, strides, batch modes, conj flags, rank-0 operands, alpha/beta) and the
 // one the specialised kernels are checked against.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "tnb_internal.h"
 
@@ -456,6 +457,183 @@ __global__ void __launch_bounds__(KRED_THREADS) einsum_kred_kernel(const KredArg
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// k-reduction on the warp-level tensor-core path (complex64 only; M = 16*MT, N = 8*NT, MT*NT <= 4).
+// With M*N = 512 the FP32-FMA kernel above sits on the ridge of the SIMT roofline (10.7 flop/B: the FMA pipe and HBM
+// both need ~2 ms for the 16 x 32 x 2^25 step of the committed Sycamore path), so neither can be hidden behind the
+// other.  Here the MACs go to `mma.sync.m16n8k8.tf32` (SASS HMMA.1688.F32.TF32) with the same error-free 3xTF32 split
+// as the tcgen05 kernels (x = hi + lo, hi = x & 0xffffe000; hi*lo + lo*hi + hi*hi; -A_im folded into the A fragment),
+// which leaves the FMA pipe idle and the kernel purely HBM-bound:
+//   * no shared-memory staging: C = A^T B with A stored [K][M], B stored [K][N] is exactly the "row x col" fragment
+//     layout of the instruction, so every lane loads its fragment elements straight from global memory (8-byte
+//     loads; a warp-wide load covers whole 64-byte runs of 4 consecutive k rows: every fetched sector is fully used);
+//   * a warp owns every 8th 8-k step of the CTA's K chunk (the 8 warps of a CTA walk one contiguous 3 KB * 8 window
+//     per iteration) and prefetches the next step's 12 registers while the 12*NT*MT MMAs of the current one issue;
+//   * the tensor core accumulates in FP32 with truncation, so a chain only lasts KRED_MMA_CHUNK steps
+//     (48 MMAs per accumulator); the chunk is then added round-to-nearest into per-warp FP32 totals in shared memory;
+//   * the 8 warps' totals are summed in a fixed order, one partial per CTA goes to the split-K workspace
+//     (same layout as the kernel above) and the deterministic reducer finishes.
+// Algorithmic bytes per launch: 8 * (M + N) * K.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KRED_MMA_CHUNK = 4;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(KRED_THREADS, 2) einsum_kred_mma_kernel(const KredArgs p) {
+    constexpr int M = 16 * MT, N = 8 * NT, R = MT * NT * 8;      // R accumulator registers per lane
+    __shared__ float tot[KRED_THREADS / 32][R][32];
+    const float2* __restrict__ A = (const float2*)p.A;
+    const float2* __restrict__ B = (const float2*)p.B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t k_begin = (int64_t)blockIdx.x * p.kchunk;
+    const int64_t k_end = (k_begin + p.kchunk) < p.K ? (k_begin + p.kchunk) : p.K;
+    const int64_t nstep = k_begin < k_end ? (k_end - k_begin + 7) / 8 : 0;
+    const float sa = p.conjA ? -1.f : 1.f, sb = p.conjB ? -1.f : 1.f;
+
+#pragma unroll
+    for (int r = 0; r < R; r++) tot[warp][r][lane] = 0.f;
+
+    float2 ra[MT][4], rb[NT][2];                                  // raw fragment elements of one step
+    auto fetch = [&](int64_t step) {
+        const int64_t k0 = k_begin + step * 8 + t, k1 = k0 + 4;
+        const bool v0 = k0 < k_end, v1 = k1 < k_end;
+        const float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < MT; i++) {
+            const float2* a0 = A + k0 * M + i * 16 + g;
+            const float2* a1 = A + k1 * M + i * 16 + g;
+            ra[i][0] = v0 ? __ldcs(a0) : z;       // (row g,     k = t)
+            ra[i][1] = v0 ? __ldcs(a0 + 8) : z;   // (row g + 8, k = t)
+            ra[i][2] = v1 ? __ldcs(a1) : z;       // (row g,     k = t + 4)
+            ra[i][3] = v1 ? __ldcs(a1 + 8) : z;   // (row g + 8, k = t + 4)
+        }
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            rb[j][0] = v0 ? __ldcs(B + k0 * N + j * 8 + g) : z;   // (k = t,     col g)
+            rb[j][1] = v1 ? __ldcs(B + k1 * N + j * 8 + g) : z;   // (k = t + 4, col g)
+        }
+    };
+
+    float acc[MT][NT][2][4];
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[i][j][c][q] = 0.f;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int r = ((i * NT + j) * 2 + c) * 4 + q;
+                        tot[warp][r][lane] += acc[i][j][c][q];
+                        acc[i][j][c][q] = 0.f;
+                    }
+    };
+
+    int in_chunk = 0;
+    if (warp < nstep) fetch(warp);
+    for (int64_t step = warp; step < nstep; step += KRED_THREADS / 32) {
+        // split the raw elements (frees the raw registers for the prefetch of this warp's next step)
+        uint32_t are_h[MT][4], are_l[MT][4], aim_h[MT][4], aim_l[MT][4], nim_h[MT][4], nim_l[MT][4];
+        uint32_t bre_h[NT][2], bre_l[NT][2], bim_h[NT][2], bim_l[NT][2];
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                split_tf32(ra[i][q].x, are_h[i][q], are_l[i][q]);
+                split_tf32(sa * ra[i][q].y, aim_h[i][q], aim_l[i][q]);
+                nim_h[i][q] = aim_h[i][q] ^ 0x80000000u;
+                nim_l[i][q] = aim_l[i][q] ^ 0x80000000u;
+            }
+#pragma unroll
+        for (int j = 0; j < NT; j++)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                split_tf32(rb[j][q].x, bre_h[j][q], bre_l[j][q]);
+                split_tf32(sb * rb[j][q].y, bim_h[j][q], bim_l[j][q]);
+            }
+        if (step + KRED_THREADS / 32 < nstep) fetch(step + KRED_THREADS / 32);
+        // small terms first: hi*lo, lo*hi, then hi*hi.   Cre += Are Bre + (-Aim) Bim ;  Cim += Are Bim + Aim Bre
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], are_h[i], bre_l[j][0], bre_l[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], are_h[i], bim_l[j][0], bim_l[j][1]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], nim_h[i], bim_l[j][0], bim_l[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], aim_h[i], bre_l[j][0], bre_l[j][1]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], are_l[i], bre_h[j][0], bre_h[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], are_l[i], bim_h[j][0], bim_h[j][1]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], nim_l[i], bim_h[j][0], bim_h[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], aim_l[i], bre_h[j][0], bre_h[j][1]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], are_h[i], bre_h[j][0], bre_h[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], are_h[i], bim_h[j][0], bim_h[j][1]);
+            }
+#pragma unroll
+        for (int i = 0; i < MT; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                mma_tf32_16x8x8(acc[i][j][0], nim_h[i], bim_h[j][0], bim_h[j][1]);
+                mma_tf32_16x8x8(acc[i][j][1], aim_h[i], bre_h[j][0], bre_h[j][1]);
+            }
+        if (++in_chunk == KRED_MMA_CHUNK) { flush(); in_chunk = 0; }
+    }
+    flush();
+    __syncthreads();
+    // warp w sums registers r = w, w + 8, ... of all warps in warp order and writes them out.
+    // accumulator fragment: q -> (row g + 8*(q>>1), col 2t + (q&1)) of the 16 x 8 tile (i, j); c = re / im
+    float* ws = (float*)p.ws + (uint64_t)blockIdx.x * M * N * 2;
+    for (int r = warp; r < R; r += KRED_THREADS / 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < KRED_THREADS / 32; w++) s += tot[w][r][lane];
+        const int q = r & 3, c = (r >> 2) & 1, ij = r >> 3, i = ij / NT, j = ij - i * NT;
+        const int m = i * 16 + g + 8 * (q >> 1), n = j * 8 + 2 * t + (q & 1);
+        ws[((uint64_t)n * M + m) * 2 + c] = s;                      // ws[(cta*N + n)*M + m] as (re, im)
+    }
+}
+
 }  // namespace
 
 // thin path: returns number of CTAs (= splitk) or 0 if not applicable
@@ -572,12 +750,36 @@ int tnb_choose_kred(const tnb_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t
     return (int)ctas;
 }
 
+// TNB_KRED_MMA=1 routes complex64 k-reductions with M = 16*MT, N = 8*NT (MT*NT <= 4) to the mma.sync kernel.
+static bool kred_mma_enabled() {
+    static const int on = [] { const char* e = getenv("TNB_KRED_MMA"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+
 int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
     const size_t esz = tnb_dtype_size(dtype);
-    if (((uintptr_t)a.A % 16) || ((uintptr_t)a.B % 16)) return -1;
     KredArgs k;
     k.A = a.A; k.B = a.B; k.ws = a.ws; k.K = a.K; k.kchunk = a.kchunk;
     k.M = (int32_t)a.M; k.N = (int32_t)a.N; k.conjA = a.conjA; k.conjB = a.conjB;
+    if (dtype == TNB_C64 && kred_mma_enabled() && k.M % 16 == 0 && k.N % 8 == 0 && !((uintptr_t)a.A % 8) && !((uintptr_t)a.B % 8)) {
+        const int MT = k.M / 16, NT = k.N / 8;
+        k.KS = k.kslices = k.mt = k.nt = 0;
+        bool done = true;
+#define TNB_KRED_MMA_LAUNCH(MT_, NT_) einsum_kred_mma_kernel<MT_, NT_><<<(unsigned)a.splitk, KRED_THREADS, 0, ctx->stream>>>(k)
+        if (MT == 1 && NT == 4) TNB_KRED_MMA_LAUNCH(1, 4);
+        else if (MT == 2 && NT == 2) TNB_KRED_MMA_LAUNCH(2, 2);
+        else if (MT == 1 && NT == 2) TNB_KRED_MMA_LAUNCH(1, 2);
+        else if (MT == 2 && NT == 1) TNB_KRED_MMA_LAUNCH(2, 1);
+        else if (MT == 1 && NT == 1) TNB_KRED_MMA_LAUNCH(1, 1);
+        else done = false;
+#undef TNB_KRED_MMA_LAUNCH
+        if (done) {
+            ctx->launches++;
+            TNB_CUDA_CHECK(ctx, cudaGetLastError());
+            return TNB_OK;
+        }
+    }
+    if (((uintptr_t)a.A % 16) || ((uintptr_t)a.B % 16)) return -1;
     const int TM = (k.M % 4 == 0 && k.M * k.N >= 256) ? 4 : 2;     // 4 x 4 micro-tiles halve the shared-memory reads per MAC
     k.mt = k.M / TM; k.nt = k.N / 4;
     int ks = 1;

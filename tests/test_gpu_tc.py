@@ -89,10 +89,12 @@ def test_thin_reduction(ctx, dt, tol, M, N):
 
 
 @pytest.mark.parametrize("dt,tol", [(np.complex64, 1e-5), (np.complex128, 1e-13)])
-@pytest.mark.parametrize("M,N", [(8, 32), (2, 4), (16, 32), (4, 128), (6, 12)])
+@pytest.mark.parametrize("M,N", [(8, 32), (2, 4), (16, 32), (4, 128), (6, 12), (32, 16), (16, 16), (16, 8)])
 def test_k_reduction_kernel(ctx, dt, tol, M, N):
     """small M x N, huge K, dense operands with the free index fastest (the environment-closing steps of a sliced
-    path; storage is column-major like Julia): HBM-bound k-reduction kernel; ragged K, conj flags, high-rank groups."""
+    path; storage is column-major like Julia): HBM-bound k-reduction kernel; ragged K, conj flags, high-rank groups.
+    With TNB_KRED_MMA=1 in the environment the complex64 cases with M % 16 == 0, N % 8 == 0 run on the mma.sync
+    (3xTF32) variant of the kernel instead of the FP32-FMA one."""
     import tenet_jl_b200 as tb
     rng = np.random.default_rng(M * 7 + N)
     hi = np.complex128
