@@ -750,9 +750,10 @@ int tnb_choose_kred(const tnb_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t
     return (int)ctas;
 }
 
-// TNB_KRED_MMA=1 routes complex64 k-reductions with M = 16*MT, N = 8*NT (MT*NT <= 4) to the mma.sync kernel.
+// complex64 k-reductions with M = 16*MT, N = 8*NT (MT*NT <= 4) go to the mma.sync kernel (measured 2.0x the FP32-FMA
+// kernel on the 16 x 32 x 2^25 step); TNB_KRED_MMA=0 keeps everything on the FMA kernel (debug / comparison).
 static bool kred_mma_enabled() {
-    static const int on = [] { const char* e = getenv("TNB_KRED_MMA"); return e ? atoi(e) : 0; }();
+    static const int on = [] { const char* e = getenv("TNB_KRED_MMA"); return e ? atoi(e) : 1; }();
     return on != 0;
 }
 
