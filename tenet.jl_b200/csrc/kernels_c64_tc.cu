@@ -877,13 +877,18 @@ __device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 
 // BSTREAM: the small operand's planes do not fit in shared memory (N*K*16 > 64 KB): a tiny pre-pass
 // (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and lane 8 of the copy warp
 // streams one 2*B_KB stage per k-block (one bulk copy, L2-resident source) next to the A rows.
-template <int NT, bool BSTREAM>   // NT: columns of the small operand per launch, padded (16, 32, 64)
+// WIDE64 (NT = 64 only): the 6-MMA form with ONE accumulator set (F | E = 256 columns + the A ring) instead of the
+// 12-MMA form with two sets: 6 x 64 clk instead of 12 x 48 clk per k-block; the price is that the TMEM drain of a
+// tile (not its write-out) is no longer overlapped with the next tile's MMAs.
+template <int NT, bool BSTREAM, bool WIDE64 = false>   // NT: columns of the small operand per launch, padded (16, 32, 64)
 __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const StemTcArgs p, const __grid_constant__ CUtensorMap tmA) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nkb = (uint32_t)p.K / TC_BK;
     const int64_t ntiles = p.M / TC_BM;
-    constexpr bool F6 = NT <= 32;                                    // 6 wide MMAs into F/E, else 12 into re/im
+    static_assert(!WIDE64 || NT == 64, "WIDE64 is the NT = 64 variant");
+    constexpr bool F6 = NT <= 32 || WIDE64;                          // 6 wide MMAs into F/E, else 12 into re/im
+    constexpr uint32_t NSETS = WIDE64 ? 1 : 2;                       // accumulator sets in tensor memory
     constexpr int B_KB = 2 * NT * TC_BK * 4;                         // bytes of one B plane ([re | im] rows) per k-block
     const uint32_t b_plane = nkb * B_KB;                             // bytes of one B plane (all k), resident mode
 
@@ -904,7 +909,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     auto b_empty = [&](int s) { return bar0 + 8u * (2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + SK_BST + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + SK_NBARS * 8);
     constexpr uint32_t SET_COLS = F6 ? 4 * NT : 2 * NT;              // F | E (2N each), or re | im (N each)
-    constexpr uint32_t APL_COL0 = 2 * SET_COLS;                      // A plane ring behind the two accumulator sets
+    constexpr uint32_t APL_COL0 = NSETS * SET_COLS;                  // A plane ring behind the accumulator set(s)
     constexpr uint32_t USED_COLS = APL_COL0 + SK_PL_MAX * SK_APL_COLS;
     constexpr uint32_t TMEM_COLS = USED_COLS <= 256 ? 256 : 512;
 
@@ -1013,10 +1018,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         uint32_t i = 0;
         int64_t hi_next = blockIdx.x < ntiles ? p.hi[blockIdx.x] : 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
-            const uint32_t set = i & 1;
+            const uint32_t set = i % NSETS;
             const int64_t hi_cur = hi_next;
             if (t + gridDim.x < ntiles) hi_next = p.hi[t + gridDim.x];   // in flight while this tile drains
-            mbar_wait(accfull_bar(set), (i >> 1) & 1);
+            mbar_wait(accfull_bar(set), (i / NSETS) & 1);
             tc_fence_after();
             if (drains) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * SET_COLS;
@@ -1122,8 +1127,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             int ps = 0, bs = 0;
             uint32_t pphase = 0, bphase = 0, i = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
-                const uint32_t set = i & 1;
-                if (i >= 2) mbar_wait(accempty_bar(set), ((i >> 1) - 1) & 1);
+                const uint32_t set = i % NSETS;
+                if (i >= NSETS) mbar_wait(accempty_bar(set), ((i / NSETS) - 1) & 1);
                 const uint32_t d0 = tmem_base + set * SET_COLS;
                 for (uint32_t kb = 0; kb < nkb; kb++) {
                     if (BSTREAM) mbar_wait(b_full(bs), bphase);
@@ -1222,17 +1227,17 @@ __global__ void stem_bsplit_kernel(const float2* __restrict__ B, TabRef bn, TabR
     }
 }
 
-template <int NT, bool BSTREAM>
+template <int NT, bool BSTREAM, bool WIDE64 = false>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     if (sk_layout(NT, a) < 3) return -1;
     const int smem = a.off_bar + SK_NBARS * 8 + 16;
-    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
+    TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM, WIDE64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
     int64_t grid = a.M / TC_BM;
     if (grid > ctx->sm_count) grid = ctx->sm_count;
     CUtensorMap tmA;
     if (!make_operand_map(&tmA, a.A, (uint64_t)a.M, (uint64_t)a.K, a.lda))
         return tnb_set_error(ctx, TNB_ECUDA, "cuTensorMapEncodeTiled failed (M=%lld K=%d lda=%lld)", (long long)a.M, a.K, (long long)a.lda);
-    c64_tf32x3_stem_kernel<NT, BSTREAM><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a, tmA);
+    c64_tf32x3_stem_kernel<NT, BSTREAM, WIDE64><<<(unsigned)grid, SK_THREADS, smem, ctx->stream>>>(a, tmA);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
@@ -1314,6 +1319,12 @@ int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass) {
     return SK_BREP * npass * (K / TC_BK) * (128 * Nsmall) / 8;
 }
 
+// TNB_STEM_WIDE64=1: 64-column passes use the single-set 6-MMA form of the stem kernel (see WIDE64 above)
+static bool stem_wide64() {
+    static const int on = [] { const char* e = getenv("TNB_STEM_WIDE64"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+
 // returns TNB_OK, or -1 when the big operand is not 16-byte aligned / has an odd leading dimension (caller falls back).
 // ws: streamed-B workspace for ALL passes (pass e.n0 / e.N uses its slice); the pre-split runs with the first pass.
 int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass) {
@@ -1341,9 +1352,9 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass)
         }
         a.bplanes = (const uint8_t*)ws + (size_t)(e.n0 / 64) * pass_bytes;
         a.brep_stride = (int64_t)npass * pass_bytes;
-        return launch_stem_tc<64, true>(ctx, a);
+        return stem_wide64() ? launch_stem_tc<64, true, true>(ctx, a) : launch_stem_tc<64, true>(ctx, a);
     }
     if (e.N <= 16) return launch_stem_tc<16, false>(ctx, a);
     if (e.N <= 32) return launch_stem_tc<32, false>(ctx, a);
-    return launch_stem_tc<64, false>(ctx, a);
+    return stem_wide64() ? launch_stem_tc<64, false, true>(ctx, a) : launch_stem_tc<64, false>(ctx, a);
 }

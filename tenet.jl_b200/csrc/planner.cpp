@@ -229,7 +229,8 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         // several passes that re-read the big operand (still far fewer bytes than a tile kernel without overlap)
         const int64_t nper = Ns > 64 ? 64 : Ns;
         const int64_t npass = Ns / std::max<int64_t>(nper, 1);
-        const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= 8 && tnb_stem_tc_shape_ok(Mb, nper, S.K);
+        static const int64_t max_pass = [] { const char* e = getenv("TNB_STEM_MAX_PASSES"); return e ? atoll(e) : 8ll; }();
+        const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= max_pass && tnb_stem_tc_shape_ok(Mb, nper, S.K);
         const bool simt = !tcst && Ns <= 16 && S.K <= 64;
         if (!simt && !tcst) continue;
         const int64_t lo_max = simt ? std::max<int64_t>(64, 2048 / std::max<int64_t>(Ns, 1)) : 128;
