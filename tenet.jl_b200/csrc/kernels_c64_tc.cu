@@ -841,7 +841,7 @@ __host__ inline int sk_layout(int nt, StemTcArgs& a) {
     auto up = [](int x, int q) { return (x + q - 1) / q * q; };
     const int nkb = a.K / TC_BK;
     const int nruns = (TC_BM * a.N) >> a.run_shift;
-    a.off_stg = up((a.bplanes ? SK_BST : nkb) * nt * 128, 1024);
+    a.off_stg = up((a.bplanes ? (nt == 128 ? SK_BST / 2 : SK_BST) : nkb) * nt * 128, 1024);
     a.off_tab = a.off_stg + up(TC_BM * a.N * 8, 1024);
     a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
     a.off_raw = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
@@ -887,8 +887,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     const uint32_t nkb = (uint32_t)p.K / TC_BK;
     const int64_t ntiles = p.M / TC_BM;
     static_assert(!WIDE64 || NT == 64, "WIDE64 is the NT = 64 variant");
+    static_assert(NT != 128 || BSTREAM, "128-column passes exist in streamed-B mode only");
     constexpr bool F6 = NT <= 32 || WIDE64;                          // 6 wide MMAs into F/E, else 12 into re/im
-    constexpr uint32_t NSETS = WIDE64 ? 1 : 2;                       // accumulator sets in tensor memory
+    constexpr uint32_t NSETS = (WIDE64 || NT == 128) ? 1 : 2;        // accumulator sets in tensor memory
+    constexpr int BST = NT == 128 ? SK_BST / 2 : SK_BST;             // B ring stages (16 KB each at NT = 128)
     constexpr int B_KB = 2 * NT * TC_BK * 4;                         // bytes of one B plane ([re | im] rows) per k-block
     const uint32_t b_plane = nkb * B_KB;                             // bytes of one B plane (all k), resident mode
 
@@ -917,7 +919,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
         for (int s = 0; s < SK_PL_MAX; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32); }
-        for (int s = 0; s < SK_BST; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int s = 0; s < BST; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -1168,7 +1170,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                     }
                     __syncwarp();
                     if (++ps == SK_PL_MAX) { ps = 0; pphase ^= 1; }
-                    if (BSTREAM && ++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                    if (BSTREAM && ++bs == BST) { bs = 0; bphase ^= 1; }
                 }
             }
         }
@@ -1196,7 +1198,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                     mbar_wait(b_empty(bs), bphase ^ 1);
                     mbar_expect_tx(b_full(bs), 2 * B_KB);
                     bulk_g2s(smem_u32(smem + bs * 2 * B_KB), bsrc + (size_t)kb * 2 * B_KB, 2 * B_KB, b_full(bs));
-                    if (++bs == SK_BST) { bs = 0; bphase ^= 1; }
+                    if (++bs == BST) { bs = 0; bphase ^= 1; }
                 }
         }
         __syncwarp();
@@ -1309,6 +1311,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
 // Small operand resident in shared memory (N*K*16 <= 64 KB), or streamed per k-block from a pre-split copy (64 columns
 // per pass, K <= 128: the regime where the tile GEMM kernel's per-tile prologue/epilogue is not amortised).
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
+    if (Nsmall == 128) return Mbig >= 65536 && Mbig % TC_BM == 0 && K >= 64 && K <= 128 && K % TC_BK == 0;   // streamed, one set
     if (!(Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K % TC_BK == 0)) return false;
     if (K <= 128 && Nsmall * K * 16 <= 64 * 1024) return true;
     return Nsmall == 64 && K <= 128;
@@ -1342,16 +1345,20 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass)
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
     const bool stream = tnb_stem_tc_ws_elems(e.N, e.K, 1) > 0;
     if (stream) {
-        if (!ws || e.N != 64) return -1;
+        if (!ws || (e.N != 64 && e.N != 128)) return -1;
         const int nkb = e.K / TC_BK;
-        const size_t pass_bytes = (size_t)nkb * 128 * 64;
+        const size_t pass_bytes = (size_t)nkb * 128 * e.N;
         if (e.n0 == 0) {
-            stem_bsplit_kernel<64><<<dim3(nkb, npass, SK_BREP), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
+            if (e.N == 128)
+                stem_bsplit_kernel<128><<<dim3(nkb, npass, SK_BREP), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
+            else
+                stem_bsplit_kernel<64><<<dim3(nkb, npass, SK_BREP), 128, 0, ctx->stream>>>(a.B, a.bn, a.bk, e.N, e.conjB, (uint8_t*)ws);
             ctx->launches++;
             TNB_CUDA_CHECK(ctx, cudaGetLastError());
         }
-        a.bplanes = (const uint8_t*)ws + (size_t)(e.n0 / 64) * pass_bytes;
+        a.bplanes = (const uint8_t*)ws + (size_t)(e.n0 / e.N) * pass_bytes;
         a.brep_stride = (int64_t)npass * pass_bytes;
+        if (e.N == 128) return launch_stem_tc<128, true>(ctx, a);
         return stem_wide64() ? launch_stem_tc<64, true, true>(ctx, a) : launch_stem_tc<64, true>(ctx, a);
     }
     if (e.N <= 16) return launch_stem_tc<16, false>(ctx, a);

@@ -218,7 +218,13 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
     // output addresses are  hi[tile] + (tile-invariant pattern);  the pattern is sorted once here (rel) together
     // with its inverse (pos), which lets the kernel write each tile in ascending address order (coalesced).
     S.st_ok = false;
-    for (int sw = 0; sw < 2 && !S.st_ok; sw++) {
+    // TNB_STEM_N128=1: small operands whose width is a multiple of 128 (64 <= K <= 128) take 128 columns per pass
+    // (single accumulator set, the big operand is read half as often); tried before the 64-column form.
+    static const bool n128 = [] { const char* e = getenv("TNB_STEM_N128"); return e ? atoi(e) != 0 : false; }();
+    for (int att = 0; att < 4 && !S.st_ok; att++) {
+        const int sw = att >> 1;
+        const bool wide = !(att & 1);
+        if (wide && !n128) continue;
         const std::vector<Ent>& big = sw ? gn : gm;
         const std::vector<Ent>& small = sw ? gm : gn;
         const int64_t Mb = sw ? S.N : S.M, Ns = sw ? S.M : S.N;
@@ -227,7 +233,8 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         // class 1: SIMT streaming (N*K small: FP32 FMA keeps up with HBM); class 2: tensor-core stem (c64 only)
         // the tensor-core stem kernel takes <= 64 small-side columns per pass; wider small operands (<= 256) run as
         // several passes that re-read the big operand (still far fewer bytes than a tile kernel without overlap)
-        const int64_t nper = Ns > 64 ? 64 : Ns;
+        if (wide && (Ns % 128 != 0 || S.K < 64 || S.K > 128)) continue;
+        const int64_t nper = wide ? 128 : (Ns > 64 ? 64 : Ns);
         const int64_t npass = Ns / std::max<int64_t>(nper, 1);
         static const int64_t max_pass = [] { const char* e = getenv("TNB_STEM_MAX_PASSES"); return e ? atoll(e) : 8ll; }();
         const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= max_pass && tnb_stem_tc_shape_ok(Mb, nper, S.K);
@@ -249,7 +256,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         HostTable cb;
         build_table(ext, st, &cb, lo_max);
         const int64_t TM = cb.lo_size;
-        if (TM < 64 || TM > 4096 || TM * (simt ? Ns : nper) > 8192 || (TM % 2)) continue;
+        if (TM < 64 || TM > 4096 || TM * (simt ? Ns : nper) > (wide ? 16384 : 8192) || (TM % 2)) continue;
         if (!simt && TM != 128) continue;
         S.st_tc = !simt;
         std::vector<int64_t> ext2, st2;
@@ -299,6 +306,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         }
         for (int64_t v : cb.hi) if (v & 1) even = false;
         for (int64_t j = 0; j < cnt * passes && even; j += R) if (S.st_rel[(size_t)j] & 1) even = false;
+        if (wide && !additive) continue;       // the 128-column form has no room for the general rank table
         S.st_additive = additive; S.st_even = even;
         if (getenv("TNB_DEBUG_STEM"))
             fprintf(stderr, "[stem] M=%lld N=%lld K=%lld big=%lld small=%lld tc=%d swap=%d TM=%lld ncol=%lld passes=%lld run=%lld additive=%d even=%d contig=%d\n",
