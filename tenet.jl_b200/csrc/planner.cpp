@@ -218,9 +218,10 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
     // output addresses are  hi[tile] + (tile-invariant pattern);  the pattern is sorted once here (rel) together
     // with its inverse (pos), which lets the kernel write each tile in ascending address order (coalesced).
     S.st_ok = false;
-    // TNB_STEM_N128=1: small operands whose width is a multiple of 128 (64 <= K <= 128) take 128 columns per pass
-    // (single accumulator set, the big operand is read half as often); tried before the 64-column form.
-    static const bool n128 = [] { const char* e = getenv("TNB_STEM_N128"); return e ? atoi(e) != 0 : false; }();
+    // Small operands whose width is a multiple of 128 (64 <= K <= 128) take 128 columns per pass (single accumulator
+    // set, the big operand is read half as often, up to 16 passes); tried before the 64-column form (<= 8 passes).
+    // TNB_STEM_N128=0 disables the 128-column form, TNB_STEM_MAX_PASSES overrides both pass limits (experiments).
+    static const bool n128 = [] { const char* e = getenv("TNB_STEM_N128"); return e ? atoi(e) != 0 : true; }();
     for (int att = 0; att < 4 && !S.st_ok; att++) {
         const int sw = att >> 1;
         const bool wide = !(att & 1);
@@ -236,7 +237,8 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         if (wide && (Ns % 128 != 0 || S.K < 64 || S.K > 128)) continue;
         const int64_t nper = wide ? 128 : (Ns > 64 ? 64 : Ns);
         const int64_t npass = Ns / std::max<int64_t>(nper, 1);
-        static const int64_t max_pass = [] { const char* e = getenv("TNB_STEM_MAX_PASSES"); return e ? atoll(e) : 8ll; }();
+        static const int64_t max_pass_env = [] { const char* e = getenv("TNB_STEM_MAX_PASSES"); return e ? atoll(e) : 0ll; }();
+        const int64_t max_pass = max_pass_env > 0 ? max_pass_env : (wide ? 16 : 8);
         const bool tcst = cplx && elem_size == 8 && Ns % nper == 0 && npass <= max_pass && tnb_stem_tc_shape_ok(Mb, nper, S.K);
         const bool simt = !tcst && Ns <= 16 && S.K <= 64;
         if (!simt && !tcst) continue;
