@@ -812,6 +812,7 @@ constexpr int SK_RAW_STAGE = TC_BK * TC_BM * 8;            // 8 KB
 constexpr int SK_APL_COLS = 4 * TC_BK;                     // TMEM columns of one A stage: planes rh | rl | ih | il, 8 k each
 constexpr int SK_BREP = 1;                      // streamed-B mode: replicas of the pre-split planes in global memory (CTA b reads
                                                 // replica b % SK_BREP, so that 148 SMs do not hammer the same 64 L2 lines at once)
+constexpr int SK_KCB = 16;                      // k-blocks per TMEM chunk (chain of <= 96 MMAs per accumulator), as in the GEMM kernel
 constexpr int SK_BST = 8;                       // streamed-B mode: stages of the B plane ring (2 planes x 2*NT rows per k-block)
 constexpr int SK_NBARS = 2 * SK_RAW_MAX + 2 * SK_PL_MAX + 4 + 2 * SK_BST;
 constexpr int SK_BUDGET = 227 * 1024;
@@ -1018,12 +1019,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         const uint32_t swz_t = sk_swz((uint32_t)etid * 2u);
         const bool odd = (swz_t & 1u) != 0;                         // pair stored in swapped order (thread constant)
         uint32_t i = 0;
+        uint32_t echunk0 = 0, echunk1 = 0;                          // chunks drained so far, per accumulator set
+        const uint32_t nchunks = (nkb + SK_KCB - 1) / SK_KCB;
         int64_t hi_next = blockIdx.x < ntiles ? p.hi[blockIdx.x] : 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
             const uint32_t set = i % NSETS;
             const int64_t hi_cur = hi_next;
             if (t + gridDim.x < ntiles) hi_next = p.hi[t + gridDim.x];   // in flight while this tile drains
-            mbar_wait(accfull_bar(set), (i / NSETS) & 1);
+            // K > 128 (128-column form only): the accumulators hold one chunk of SK_KCB k-blocks at a time; chunk 0 is
+            // stored into the staging tile, later chunks are added to it round-to-nearest (each thread owns its entries)
+            for (uint32_t ch = 0; ch < nchunks; ch++) {
+            const bool rmw = ch > 0;
+            mbar_wait(accfull_bar(set), (set ? echunk1 : echunk0) & 1);
+            if (set) echunk1++; else echunk0++;
             tc_fence_after();
             if (drains) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * SET_COLS;
@@ -1055,18 +1063,27 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                             co[j] = c4.x; co[j + 1] = c4.y; co[j + 2] = c4.z; co[j + 3] = c4.w;
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            *reinterpret_cast<float2*>(stg_b + (rowoff ^ co[j])) = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
+                        for (int j = 0; j < 16; j++) {
+                            float2* d = reinterpret_cast<float2*>(stg_b + (rowoff ^ co[j]));
+                            float2 v = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
+                            if (rmw) { const float2 o = *d; v.x += o.x; v.y += o.y; }
+                            *d = v;
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            stg[tab16[(c0 + j) * TC_BM + row]] = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
+                        for (int j = 0; j < 16; j++) {
+                            float2* d = stg + tab16[(c0 + j) * TC_BM + row];
+                            float2 v = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
+                            if (rmw) { const float2 o = *d; v.x += o.x; v.y += o.y; }
+                            *d = v;
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: next-next tile may start
+            if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: the next chunk / tile may start
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile complete (epilogue warps only)
             float2* base = p.C + hi_cur;
             if (p.vec2) {
@@ -1128,17 +1145,23 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             const uint32_t a0 = tmem_base + APL_COL0;
             int ps = 0, bs = 0;
             uint32_t pphase = 0, bphase = 0, i = 0;
+            uint32_t mchunk0 = 0, mchunk1 = 0;                       // chunks started so far, per accumulator set
             for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
                 const uint32_t set = i % NSETS;
-                if (i >= NSETS) mbar_wait(accempty_bar(set), ((i / NSETS) - 1) & 1);
                 const uint32_t d0 = tmem_base + set * SET_COLS;
                 for (uint32_t kb = 0; kb < nkb; kb++) {
+                    const bool cfirst = (kb % SK_KCB) == 0, clast = (kb % SK_KCB) == SK_KCB - 1 || kb + 1 == nkb;
+                    if (cfirst) {                                    // the set must have been drained (previous chunk / tile)
+                        const uint32_t mc = set ? mchunk1 : mchunk0;
+                        if (mc >= 1) mbar_wait(accempty_bar(set), (mc - 1) & 1);
+                        if (set) mchunk1++; else mchunk0++;
+                    }
                     if (BSTREAM) mbar_wait(b_full(bs), bphase);
                     mbar_wait(apl_full(ps), pphase);
                     tc_fence_after();
                     const uint32_t a_rh = a0 + ps * SK_APL_COLS, a_rl = a_rh + 8, a_ih = a_rh + 16, a_il = a_rh + 24;
                     const uint64_t b_h = bdesc0 + (uint64_t)((BSTREAM ? 2u * bs : kb) * (B_KB >> 4)), b_l = b_h + bl_off;
-                    const uint32_t acc = kb > 0 ? 1u : 0u;
+                    const uint32_t acc = cfirst ? 0u : 1u;
                     if (elect_one()) {
                         if (F6) {
                             const uint32_t d_f = d0, d_e = d0 + 2 * NT;
@@ -1166,7 +1189,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                         }
                         umma_commit(apl_empty(ps));
                         if (BSTREAM) umma_commit(b_empty(bs));
-                        if (kb + 1 == nkb) umma_commit(accfull_bar(set));
+                        if (clast) umma_commit(accfull_bar(set));
                     }
                     __syncwarp();
                     if (++ps == SK_PL_MAX) { ps = 0; pphase ^= 1; }
@@ -1311,7 +1334,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
 // Small operand resident in shared memory (N*K*16 <= 64 KB), or streamed per k-block from a pre-split copy (64 columns
 // per pass, K <= 128: the regime where the tile GEMM kernel's per-tile prologue/epilogue is not amortised).
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K) {
-    if (Nsmall == 128) return Mbig >= 65536 && Mbig % TC_BM == 0 && K >= 64 && K <= 128 && K % TC_BK == 0;   // streamed, one set
+    if (Nsmall == 128) return Mbig >= 65536 && Mbig % TC_BM == 0 && K >= 64 && K <= 512 && K % TC_BK == 0;   // streamed, one set, TMEM chunks of 128 k
     if (!(Mbig >= 65536 && Mbig % TC_BM == 0 && Nsmall >= 16 && Nsmall <= 64 && Nsmall % 16 == 0 && K >= 8 && K % TC_BK == 0)) return false;
     if (K <= 128 && Nsmall * K * 16 <= 64 * 1024) return true;
     return Nsmall == 64 && K <= 128;

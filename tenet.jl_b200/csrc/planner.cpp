@@ -234,7 +234,9 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         // class 1: SIMT streaming (N*K small: FP32 FMA keeps up with HBM); class 2: tensor-core stem (c64 only)
         // the tensor-core stem kernel takes <= 64 small-side columns per pass; wider small operands (<= 256) run as
         // several passes that re-read the big operand (still far fewer bytes than a tile kernel without overlap)
-        if (wide && (Ns % 128 != 0 || S.K < 64 || S.K > 128)) continue;
+        // K > 128 in the 128-column form (TMEM chunks of 128 k added in the staging tile): TNB_STEM_KMAX=512 (experiment)
+        static const int64_t kmax_wide = [] { const char* e = getenv("TNB_STEM_KMAX"); return e ? atoll(e) : 128ll; }();
+        if (wide && (Ns % 128 != 0 || S.K < 64 || S.K > kmax_wide)) continue;
         const int64_t nper = wide ? 128 : (Ns > 64 ? 64 : Ns);
         const int64_t npass = Ns / std::max<int64_t>(nper, 1);
         static const int64_t max_pass_env = [] { const char* e = getenv("TNB_STEM_MAX_PASSES"); return e ? atoll(e) : 0ll; }();

@@ -241,3 +241,26 @@ def test_stem_tc_rank_table_path(ctx, monkeypatch):
         r = np.transpose(ref, [(big + ["n"]).index(i) for i in out])
         err = np.abs(c.parent - r).max() / np.abs(r).max()
         assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("N,K", [(128, 256), (256, 512), (128, 200)])
+def test_stem_tc_long_k(ctx, N, K):
+    """huge x small with K > 128: the tile GEMM kernel by default; with TNB_STEM_KMAX=512 in the environment the
+    128-column stem passes take K <= 512 in TMEM chunks of 128 k that are added in the staging tile.  Both accumulate
+    chunks round-to-nearest, so the bound is the same."""
+    import os
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(N + K)
+    a = crand(rng, (2,) * 17 + (K,))
+    b = crand(rng, (N, K))
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"])
+    hi = np.complex128
+    ref = np.tensordot(a.astype(hi), b.astype(hi), axes=([17], [1]))
+    kmax = int(os.environ.get("TNB_STEM_KMAX", "128"))
+    for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8]]:
+        c = tb.binary_einsum(ta, tb_, out=out)
+        assert ctx.last_kernel == ("stem_tc" if K <= kmax and K % 8 == 0 else "c64_tf32x3"), ctx.last_kernel
+        r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        err = np.abs(c.parent - r).max() / np.abs(r).max()
+        assert err < 1e-5, err
