@@ -179,11 +179,16 @@ def test_committed_path_kernel_selection(built_lib):
         si = plan.step_info(s)
         if not si["hoisted"]:
             flops[si["kernel_name"]] = flops.get(si["kernel_name"], 0.0) + si["flops"]
+            # K <= 128 huge x small steps (small side a multiple of 128, <= 16 passes) belong to the stem kernel's
+            # 128-column passes, not to the tile GEMM kernel (measured 136 -> 186 TFLOP/s on 262144 x 2048 x 128)
+            if si["kernel_name"] == "c64_tf32x3" and si["flops"] > 1e11:
+                assert si["K"] > 128, si
     tot = sum(flops.values())
     assert abs(tot - info["flops_per_slice"]) / tot < 1e-9
     tc = flops.get("c64_tf32x3", 0) + flops.get("stem_tc", 0)
     assert tc / tot > 0.98, flops                              # tensor-core kernels carry the flops
     assert flops.get("generic", 0) + flops.get("splitk", 0) < 1e-3 * tot, flops
+    assert flops.get("stem_tc", 0) > 0.45 * tot, flops
     assert "stream" in flops                                   # the environment-closing k-reduction step
     assert info["workspace_bytes"] < 64 * 2 ** 30              # arena + workspace fit one B200 with room to spare
 
