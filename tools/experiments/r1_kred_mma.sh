@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call: GPU test suite, default bench line, the TNB_KRED_MMA=1 variant (tests + bench), one more workload,
 # smoke, full ncu captures of both k-reduction kernels.  Everything lands in gpurun_out/.
-#   gpurun --timeout 780 -- 'bash tools/gpu_round.sh'
+#   gpurun --timeout 780 -- 'bash tools/experiments/r1_kred_mma.sh'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/smi.txt 2>&1
 timeout 400 python -m pytest tests -m gpu -q -rA --durations=20 > gpurun_out/pytest_gpu.log 2>&1
