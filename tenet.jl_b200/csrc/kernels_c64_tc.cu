@@ -775,7 +775,8 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 64 per pass, K <= 128.
+// Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 128 per pass, K <= 128
+// (K <= 512 in chunks for the 128-column form).
 //
 // These steps carry most of the BYTES of a good sliced path (arithmetic intensity 13-64 flop/B, around the ridge).
 // Round-1 profiling (profiles/r1_summary.md) showed the first version of this kernel was bound by SHARED-MEMORY
@@ -799,7 +800,17 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
 //     shared staging tile, and write the tile to C in ascending address order, 16 B per thread — coalesced whatever
 //     layout the consumer asked for.  When the rank is separable on disjoint bits, rank(row,col) = r(row) ^ c(col)
 //     (always for power-of-two extents), it comes from one register and a broadcast column table.
-// Chain length in TMEM is <= 6*K/8 = 96 MMAs per accumulator (K <= 128): round-toward-zero bias ~6e-6 relative.
+//       N = 128: 12 MMAs of width 128 (64 clk each: the 45.5-clk floor of narrow MMAs no longer bites) into ONE set of
+//                256 columns (re | im) next to the A ring; streamed-B mode only (16 KB B stages, 4-stage ring), 128 KB
+//                staging tile, separable ranks only.  The big operand is read once per 128 columns and the TMEM drain
+//                of a tile (not its write-out) is exposed (~10 % of a K = 128 tile).  Default for small operands whose
+//                width is a multiple of 128 (planner.cpp); measured 205-216 TFLOP/s vs 170-176 for two 64-column passes;
+//       WIDE64:  N = 64 with the 6-MMA form and one set (experiment, TNB_STEM_WIDE64=1: neutral);
+//   * two accumulator sets (one for N = 128 / WIDE64): 8 epilogue warps drain one (tcgen05.ld) while the MMAs fill the
+//     other (see above for the drain/write-out pipeline);
+//   * K > 128 (N = 128 form, TNB_STEM_KMAX): the accumulators hold one chunk of SK_KCB = 16 k-blocks at a time; chunk 0 is
+//     stored into the staging tile, later chunks are added to it round-to-nearest (same chunking as the GEMM kernel).
+// Chain length in TMEM is <= 6*128/8 = 96 MMAs per accumulator (one chunk): round-toward-zero bias ~6e-6 relative.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SK_WORKERS = 256;                 // warps 0-7
 constexpr int SK_EPI = 256;                     // warps 8-15: two per TMEM lane quarter, each takes half of the columns

@@ -9,7 +9,7 @@ import tenet_jl_b200 as tb
 from tools.make_paths import network
 
 # measured (profiles/r1_summary.md): flop/s, byte/s, fixed launch cost
-RATES = {"c64_tf32x3": (185e12, 3.0e12), "stem_tc": (150e12, 4.0e12), "stem": (40e12, 4.2e12), "stream": (20e12, 2.8e12),
+RATES = {"c64_tf32x3": (187e12, 3.0e12), "stem_tc": (190e12, 4.2e12), "stem": (40e12, 4.2e12), "stream": (50e12, 4.8e12),
          "generic": (25e12, 1.5e12), "splitk": (25e12, 1.5e12), "c128_dmma": (19e12, 3e12)}
 LAUNCH = 4e-6
 
