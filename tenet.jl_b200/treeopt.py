@@ -241,11 +241,54 @@ def tree_time_cost(net: _Net, steps, removed: int = 0) -> float:
     return tot
 
 
+def slice_with_reconfiguration(net: _Net, inputs, sizes, output, steps, target_log2_size: float, reconf_size: int,
+                               minimize: str, rng, max_slices_log2: float = 40.0):
+    """Interleaved slicing (the `slicing_reconf` idea of hyper-optimisers): slice ONE index — the one, among the indices
+    of the largest intermediates, whose removal gives the lowest total cost over all slices (ties: smaller peak) — then
+    re-optimise the tree for the sliced network with one round of subtree reconfiguration, and repeat until the peak
+    fits.  Returns (steps, chosen labels, removed mask)."""
+    from .pathfinder import _intermediate_masks
+    removed, chosen, lg_slices = 0, [], 0.0
+    lm, ls, _ = path_cost(net, steps, removed)
+
+    def total_cost(st, rem, lgs):
+        return (tree_time_cost(net, st, rem) if minimize == "time" else path_cost(net, st, rem)[0]) + lgs
+
+    while ls > target_log2_size and lg_slices < max_slices_log2:
+        cand = 0
+        for m in _intermediate_masks(net, steps, removed):
+            if net.lsize(m) >= ls - 1.0 - 1e-9:          # indices of the (near-)largest intermediates
+                cand |= m
+        cand &= ~net.out
+        if not cand:
+            break
+        best = None
+        for low in _popbits(cand):
+            r2 = removed | low
+            _, ls2, _ = path_cost(net, steps, r2)
+            key = (total_cost(steps, r2, lg_slices + net.lg[low.bit_length() - 1]), ls2)
+            if best is None or key < best[0]:
+                best = (key, low)
+        low = best[1]
+        removed |= low
+        lab = net.labels[low.bit_length() - 1]
+        chosen.append(lab)
+        lg_slices += math.log2(sizes[lab])
+        s2 = subtree_reconfigure(net, steps, removed, reconf_size, 1, minimize, rng)
+        _, ls2, _ = path_cost(net, s2, removed)
+        _, ls1, _ = path_cost(net, steps, removed)
+        if ls2 <= max(ls1, target_log2_size) + 1e-9 and total_cost(s2, removed, lg_slices) <= total_cost(steps, removed, lg_slices):
+            steps = s2
+        lm, ls, _ = path_cost(net, steps, removed)
+    return steps, chosen, removed
+
+
 def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, target_log2_size: Optional[float] = None,
                  reconf_size: int = 8, reconf_rounds: int = 2, keep: int = 4, verbose: bool = False,
-                 minimize: str = "flops") -> ContractionPath:
+                 minimize: str = "flops", slicing: str = "greedy") -> ContractionPath:
     """Randomised greedy restarts -> subtree reconfiguration of the best few -> greedy slicing with
-    reconfiguration of the sliced tree.  Returns the best (total MACs over all slices) path found."""
+    reconfiguration of the sliced tree (slicing="greedy"), or slicing interleaved with reconfiguration
+    (slicing="interleaved").  Returns the best (total MACs over all slices) path found."""
     from .pathfinder import find_slices
     net = _Net(inputs, sizes, output)
     rng = random.Random(seed)
@@ -265,7 +308,16 @@ def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, tar
             print(f"  greedy 2^{lm:.2f}/2^{ls:.0f} -> reconf 2^{lm2:.2f}/2^{ls2:.0f}")
         p = ContractionPath(s2, (), tuple(output), lm2, ls2, 1, {})
         if target_log2_size is not None and ls2 > target_log2_size:
-            p = find_slices(inputs, sizes, output, p, target_log2_size)
+            if slicing == "interleaved":
+                st, chosen, removed = slice_with_reconfiguration(net, inputs, sizes, output, s2, target_log2_size,
+                                                                 reconf_size, minimize, rng)
+                lmi, lsi, _ = path_cost(net, st, removed)
+                ns = 1
+                for i in chosen:
+                    ns *= sizes[i]
+                p = ContractionPath(list(st), tuple(chosen), tuple(output), lmi, lsi, ns, {})
+            else:
+                p = find_slices(inputs, sizes, output, p, target_log2_size)
             removed = sum(1 << net.bit[i] for i in p.sliced)
             s3 = subtree_reconfigure(net, p.steps, removed, reconf_size, reconf_rounds, minimize, rng)
             lm3, ls3, _ = path_cost(net, s3, removed)

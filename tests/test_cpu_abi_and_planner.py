@@ -164,6 +164,29 @@ def test_pathfinder_costs_and_slicing():
     assert abs(np.log2(float(m3)) - bp.log2_macs) < 1e-6 and abs(np.log2(float(x3)) - bp.log2_max_size) < 1e-6
 
 
+@pytest.mark.parametrize("slicing", ["greedy", "interleaved"])
+def test_hyper_search_sliced_paths_are_valid_and_exact(slicing):
+    """tree search with both slicing strategies: the advertised costs match an independent recount, the peak fits the
+    target, and the sliced contraction (oracle, complex128) equals the unsliced one."""
+    import tenet_jl_b200 as tb
+    from tenet_jl_b200 import treeopt
+    tn = tb.workloads.random_regular_network(n=60, bond=2, dtype=np.complex128, seed=11)
+    inputs = [t.inds for t in tn.tensors]
+    sizes = tn.sizes()
+    p0 = tb.optimize_path(inputs, sizes, (), ntrials=8, seed=0)
+    target = p0.log2_max_size - 3
+    assert target >= 5                      # a handful of slices, not thousands (the oracle loops over them)
+    p = treeopt.hyper_search(inputs, sizes, (), ntrials=16, seed=2, target_log2_size=target, reconf_size=6,
+                             reconf_rounds=1, keep=2, minimize="time", slicing=slicing)
+    assert 2 <= p.nslices <= 1024 and p.log2_max_size <= target + 1e-9
+    macs, mx, _ = orc.path_flops(inputs, sizes, p.steps, sliced=p.sliced)
+    assert abs(np.log2(float(macs)) - p.log2_macs) < 1e-6 and abs(np.log2(float(mx)) - p.log2_max_size) < 1e-6
+    arrays = [t.parent for t in tn.tensors]
+    full, _ = orc.contract_path(arrays, inputs, p0.steps)
+    sl, _ = orc.contract_sliced(arrays, inputs, p.steps, list(p.sliced))
+    assert abs(complex(sl) - complex(full)) < 1e-10 * max(abs(complex(full)), 1e-30)
+
+
 def test_committed_path_kernel_selection(built_lib):
     """dry plan of the committed 53-qubit path: the planner must route the work to the kernels bench.py reports on
     (no silent fall-back of a big step to the generic kernel), with the workspace the streamed-B / split-K steps need."""

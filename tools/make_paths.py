@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--method", default="hyper", choices=["hyper", "greedy"])
     ap.add_argument("--keep", type=int, default=8)
     ap.add_argument("--reconf-size", type=int, default=9)
+    ap.add_argument("--slicing", default="greedy", choices=["greedy", "interleaved"])
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     tn = network(a.name)
@@ -50,7 +51,8 @@ def main():
     if a.method == "hyper":
         from tenet_jl_b200 import treeopt
         p = treeopt.hyper_search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
-                                 reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True, minimize=a.minimize)
+                                 reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True, minimize=a.minimize,
+                                 slicing=a.slicing)
     else:
         p = tb.pathfinder.search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
                                  minimize=a.minimize)
