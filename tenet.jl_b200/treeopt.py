@@ -285,7 +285,7 @@ def slice_with_reconfiguration(net: _Net, inputs, sizes, output, steps, target_l
 
 def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, target_log2_size: Optional[float] = None,
                  reconf_size: int = 8, reconf_rounds: int = 2, keep: int = 4, verbose: bool = False,
-                 minimize: str = "flops", slicing: str = "greedy") -> ContractionPath:
+                 minimize: str = "flops", slicing: str = "greedy", prescreen: int = 0) -> ContractionPath:
     """Randomised greedy restarts -> subtree reconfiguration of the best few -> greedy slicing with
     reconfiguration of the sliced tree (slicing="greedy"), or slicing interleaved with reconfiguration
     (slicing="interleaved").  Returns the best (total MACs over all slices) path found."""
@@ -300,9 +300,24 @@ def hyper_search(inputs, sizes, output=(), ntrials: int = 64, seed: int = 0, tar
         lm, ls, _ = path_cost(net, steps, 0)
         cands.append((lm, ls, steps))
     cands.sort(key=lambda c: (c[0], c[1]))
+    pre_rounds = 0
+    if prescreen > keep:
+        # the greedy cost is a poor predictor of where reconfiguration ends up (the committed Sycamore tree started as
+        # the 200th-best greedy tree: 2^59 -> 2^47.8): give MANY candidates one cheap round, keep the best few after it
+        pre = []
+        for lm, ls, steps in cands[:prescreen]:
+            s1 = subtree_reconfigure(net, steps, 0, reconf_size, 1, minimize, rng)
+            c1 = tree_time_cost(net, s1, 0) if minimize == "time" else path_cost(net, s1, 0)[0]
+            l1, z1, _ = path_cost(net, s1, 0)
+            pre.append((c1, l1, z1, s1))
+        pre.sort(key=lambda c: c[0])
+        if verbose:
+            print("  prescreen (1 round): " + " ".join(f"{c[0]:.1f}" for c in pre[:12]))
+        cands = [(c[1], c[2], c[3]) for c in pre]
+        pre_rounds = 1
     best = None
     for lm, ls, steps in cands[:keep]:
-        s2 = subtree_reconfigure(net, steps, 0, reconf_size, reconf_rounds, minimize, rng)
+        s2 = subtree_reconfigure(net, steps, 0, reconf_size, max(1, reconf_rounds - pre_rounds), minimize, rng)
         lm2, ls2, _ = path_cost(net, s2, 0)
         if verbose:
             print(f"  greedy 2^{lm:.2f}/2^{ls:.0f} -> reconf 2^{lm2:.2f}/2^{ls2:.0f}")

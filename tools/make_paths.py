@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--keep", type=int, default=8)
     ap.add_argument("--reconf-size", type=int, default=9)
     ap.add_argument("--slicing", default="greedy", choices=["greedy", "interleaved"])
+    ap.add_argument("--prescreen", type=int, default=0, help="give this many greedy trees one reconfiguration round before keeping --keep")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     tn = network(a.name)
@@ -52,7 +53,7 @@ def main():
         from tenet_jl_b200 import treeopt
         p = treeopt.hyper_search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
                                  reconf_size=a.reconf_size, reconf_rounds=3, keep=a.keep, verbose=True, minimize=a.minimize,
-                                 slicing=a.slicing)
+                                 slicing=a.slicing, prescreen=a.prescreen)
     else:
         p = tb.pathfinder.search(inputs, sizes, (), ntrials=a.trials, seed=a.seed, target_log2_size=a.target,
                                  minimize=a.minimize)
