@@ -46,6 +46,7 @@ extern "C" {
 /* precision policy for ComplexF32 / Float32 tensor-core GEMM steps (tnb_ctx_set_option) */
 #define TNB_OPT_C64_MODE     1   /* value: TNB_C64_SIMT | TNB_C64_TF32X3 | TNB_C64_TF32X3_FAST */
 #define TNB_OPT_FORCE_KERNEL 2   /* value: 0 auto, 1 generic table kernel only (debug/parity) */
+#define TNB_OPT_GEMM_PAIR    3   /* value: 1 (default) c64 GEMM steps on CTA pairs (cta_group::2), 0 the 1-CTA kernel */
 #define TNB_C64_SIMT   0         /* exact FP32 FMA (BLAS-equivalent rounding)                  */
 #define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo split; TMEM chunks of 64 k drained into RN fp32 totals (default) */
 #define TNB_C64_TF32X3_FAST 2    /* same, whole K chained in TMEM (RZ accumulate bias ~6e-8 * 0.75 K relative) */
@@ -194,6 +195,7 @@ int tnb_contract_path(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nleaves,
 int tnb_comm_unique_id(void* id128);
 int tnb_comm_init(tnb_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
 int tnb_comm_allreduce_sum(tnb_ctx* ctx, tnb_buf* buf, size_t offset_bytes, int64_t count, int32_t dtype);
+int32_t tnb_comm_size(const tnb_ctx* ctx);   /* ranks of the communicator bound to ctx; 1 when none */
 int tnb_comm_destroy(tnb_ctx* ctx);
 
 #ifdef __cplusplus

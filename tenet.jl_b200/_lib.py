@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtnb200.so")
 
 TNB_OK, TNB_EINVAL, TNB_ENOMEM, TNB_ECUDA, TNB_ENCCL, TNB_EUNSUPPORTED = range(6)
 TNB_C128, TNB_C64, TNB_F64, TNB_F32 = range(4)
-TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL = 1, 2
+TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL, TNB_OPT_GEMM_PAIR = 1, 2, 3
 TNB_C64_SIMT, TNB_C64_TF32X3, TNB_C64_TF32X3_FAST = 0, 1, 2
 KERNEL_NAMES = {0: "generic", 1: "c64_tf32x3", 2: "c128_dmma", 3: "stream", 4: "splitk", 5: "stem", 6: "stem_tc"}
 
@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "tnb_buf_bytes", "tnb_mem_stats", "tnb_mem_trim", "tnb_binary_einsum", "tnb_binary_einsum_result",
     "tnb_plan_create", "tnb_plan_create_dry", "tnb_plan_execute", "tnb_plan_destroy", "tnb_plan_get_info",
     "tnb_plan_get_step", "tnb_plan_profile", "tnb_plan_get_step_time", "tnb_plan_dump_table", "tnb_plan_dump_step", "tnb_contract_path", "tnb_comm_unique_id",
-    "tnb_comm_init", "tnb_comm_allreduce_sum", "tnb_comm_destroy",
+    "tnb_comm_init", "tnb_comm_allreduce_sum", "tnb_comm_size", "tnb_comm_destroy",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def load_library():
             "tnb_comm_unique_id": (C.c_int, [vp]),
             "tnb_comm_init": (C.c_int, [vp, vp, i32, i32]),
             "tnb_comm_allreduce_sum": (C.c_int, [vp, vp, sz, i64, i32]),
+            "tnb_comm_size": (i32, [vp]),
             "tnb_comm_destroy": (C.c_int, [vp]),
         }
         for name, (res, args) in sig.items():

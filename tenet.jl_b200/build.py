@@ -16,7 +16,7 @@ FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=s
 
 def _deps():
     csrc = os.path.join(HERE, "csrc")
-    deps = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cpp", ".h")))
+    deps = sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cpp", ".h", ".inc")))
     deps.append(os.path.join(HERE, "..", "include", "tnb200.h"))
     return [d for d in deps if os.path.exists(d)]
 

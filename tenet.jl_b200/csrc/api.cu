@@ -241,17 +241,24 @@ extern "C" {
 int tnb_binary_einsum_result(const tnb_tensor* A, const tnb_tensor* B, const int32_t* sum_modes, int32_t nsum,
                              int32_t* out_rank, int32_t* out_modes, int64_t* out_extents) {
     if (!A || !B || !out_rank || !out_modes || !out_extents) return TNB_EINVAL;
+    if (A->rank < 0 || A->rank > TNB_MAX_RANK || B->rank < 0 || B->rank > TNB_MAX_RANK) return TNB_EUNSUPPORTED;
+    if ((A->rank > 0 && (!A->mode || !A->extent)) || (B->rank > 0 && (!B->mode || !B->extent))) return TNB_EINVAL;
     std::set<int32_t> sum(sum_modes, sum_modes + (sum_modes ? nsum : 0));
     std::set<int32_t> inA(A->mode, A->mode + A->rank), inB(B->mode, B->mode + B->rank);
     int n = 0;
+    // out_modes / out_extents hold TNB_MAX_RANK entries: check before every store
+    auto put = [&](int32_t mode, int64_t ext) {
+        if (n >= TNB_MAX_RANK) return false;
+        out_modes[n] = mode; out_extents[n++] = ext;
+        return true;
+    };
     // free(A) in A's order, free(B) in B's order, then batch modes in A's order
     for (int r = 0; r < A->rank; r++)
-        if (!sum.count(A->mode[r]) && !inB.count(A->mode[r])) { out_modes[n] = A->mode[r]; out_extents[n++] = A->extent[r]; }
+        if (!sum.count(A->mode[r]) && !inB.count(A->mode[r]) && !put(A->mode[r], A->extent[r])) return TNB_EUNSUPPORTED;
     for (int r = 0; r < B->rank; r++)
-        if (!sum.count(B->mode[r]) && !inA.count(B->mode[r])) { out_modes[n] = B->mode[r]; out_extents[n++] = B->extent[r]; }
+        if (!sum.count(B->mode[r]) && !inA.count(B->mode[r]) && !put(B->mode[r], B->extent[r])) return TNB_EUNSUPPORTED;
     for (int r = 0; r < A->rank; r++)
-        if (!sum.count(A->mode[r]) && inB.count(A->mode[r])) { out_modes[n] = A->mode[r]; out_extents[n++] = A->extent[r]; }
-    if (n > TNB_MAX_RANK) return TNB_EUNSUPPORTED;
+        if (!sum.count(A->mode[r]) && inB.count(A->mode[r]) && !put(A->mode[r], A->extent[r])) return TNB_EUNSUPPORTED;
     *out_rank = n;
     return TNB_OK;
 }
@@ -505,15 +512,21 @@ int tnb_plan_execute(tnb_ctx* ctx, tnb_plan* P, int64_t slice_begin, int64_t sli
     int rc;
     bool acc = accumulate != 0;
     const bool root_hoisted = P->steps[P->nsteps - 1].hoisted;
+    // accumulate = 0 means out = sum of the requested slices: an empty range (a rank that owns no slice) is zeros
+    auto zero_out = [&]() -> int {
+        const PlanTensor& ot = P->nodes[root].t;
+        return tnb_launch_zero_strided(ctx, dtype, (char*)P->out_buf->ptr + (size_t)P->out_off * esz, (int)ot.ext.size(),
+                                       ot.ext.data(), ot.stride.data());
+    };
     if (root_hoisted) {
         // no slice dependence at all: one pass (a rank with an empty slice range contributes nothing)
-        if (slice_begin != 0) return TNB_OK;
+        if (slice_begin != 0) return acc ? TNB_OK : zero_out();
         for (int s : P->order_hoisted)
             if ((rc = run(s, acc))) return rc;
         collect();
         return TNB_OK;
     }
-    if (slice_begin >= slice_end) return TNB_OK;
+    if (slice_begin >= slice_end) return acc ? TNB_OK : zero_out();
     for (int s : P->order_hoisted)
         if ((rc = run(s, false))) return rc;
     collect();

@@ -103,6 +103,10 @@ int tnb_comm_allreduce_sum(tnb_ctx* ctx, tnb_buf* buf, size_t offset_bytes, int6
     return TNB_OK;
 }
 
+// ranks of the communicator bound to this context (1 when none): lets a caller whose launcher says world > 1 refuse to
+// return a PARTIAL slice sum when tnb_comm_init was never called on this context
+int32_t tnb_comm_size(const tnb_ctx* ctx) { return (ctx && ctx->comm) ? ctx->nranks : 1; }
+
 int tnb_comm_destroy(tnb_ctx* ctx) {
     if (!ctx) return TNB_EINVAL;
     if (ctx->comm && ctx->nccl) {

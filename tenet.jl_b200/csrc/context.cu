@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "tnb_internal.h"
 
 static thread_local std::string g_create_error;
@@ -45,6 +46,7 @@ int tnb_ctx_create(int device, tnb_ctx** out) {
     if (!ctx) return tnb_set_error(nullptr, TNB_ENOMEM, "host allocation failed");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("TNB_GEMM_PAIR")) ctx->gemm_pair = atoi(e) ? 1 : 0;   // default of TNB_OPT_GEMM_PAIR
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return tnb_set_error(nullptr, TNB_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -77,6 +79,9 @@ int tnb_ctx_set_option(tnb_ctx* ctx, int option, int64_t value) {
             return TNB_OK;
         case TNB_OPT_FORCE_KERNEL:
             ctx->force_generic = value ? 1 : 0;
+            return TNB_OK;
+        case TNB_OPT_GEMM_PAIR:
+            ctx->gemm_pair = value ? 1 : 0;
             return TNB_OK;
     }
     return tnb_set_error(ctx, TNB_EINVAL, "unknown option %d", option);

@@ -774,6 +774,8 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
     return TNB_OK;
 }
 
+#include "pair_kernel.inc"
+
 // ---------------------------------------------------------------------------------------------------------
 // Persistent tensor-core STEM kernel: huge dense operand x small operand,  M huge, 16 <= N <= 128 per pass, K <= 128
 // (K <= 512 in chunks for the 128-column form).
@@ -1338,6 +1340,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
         return launch_tc<128>(ctx, a);
     }
     if (!tc_acc_ok(a)) return -1;
+    if (ctx->gemm_pair && a.M > (uint32_t)TC_BM) return launch_tc_pair(ctx, a);   // CTA pairs on 256 x 128 tiles
     return launch_tc_acc(ctx, a);
 }
 

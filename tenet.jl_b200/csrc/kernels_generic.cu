@@ -762,7 +762,9 @@ int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
     KredArgs k;
     k.A = a.A; k.B = a.B; k.ws = a.ws; k.K = a.K; k.kchunk = a.kchunk;
     k.M = (int32_t)a.M; k.N = (int32_t)a.N; k.conjA = a.conjA; k.conjB = a.conjB;
-    if (dtype == TNB_C64 && kred_mma_enabled() && k.M % 16 == 0 && k.N % 8 == 0 && !((uintptr_t)a.A % 8) && !((uintptr_t)a.B % 8)) {
+    // TNB_C64_SIMT is the exact-FP32 policy: it must not see tensor-core rounding on the amplitude-closing steps either
+    const bool simt_only = ctx && ctx->c64_mode == TNB_C64_SIMT;
+    if (dtype == TNB_C64 && !simt_only && kred_mma_enabled() && k.M % 16 == 0 && k.N % 8 == 0 && !((uintptr_t)a.A % 8) && !((uintptr_t)a.B % 8)) {
         const int MT = k.M / 16, NT = k.N / 8;
         k.KS = k.kslices = k.mt = k.nt = 0;
         bool done = true;
@@ -801,6 +803,36 @@ int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& a) {
     if (dtype == TNB_C64) { if (TM == 4) TNB_KRED_LAUNCH(float2, 4); else TNB_KRED_LAUNCH(float2, 2); }
     else { if (TM == 4) TNB_KRED_LAUNCH(double2, 4); else TNB_KRED_LAUNCH(double2, 2); }
 #undef TNB_KRED_LAUNCH
+    ctx->launches++;
+    TNB_CUDA_CHECK(ctx, cudaGetLastError());
+    return TNB_OK;
+}
+
+// Strided zero fill of an output view (tnb_plan_execute with accumulate = 0 and an empty slice range: the header
+// contract "out = sum of the requested slices" means zeros, also for non-dense views).
+struct ZeroArgs { int32_t rank; int64_t total; int64_t ext[TNB_MAX_RANK]; int64_t stride[TNB_MAX_RANK]; };
+template <typename T>
+__global__ void zero_strided_kernel(T* __restrict__ base, const ZeroArgs z) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < z.total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i, off = 0;
+        for (int d = 0; d < z.rank; d++) { off += (r % z.ext[d]) * z.stride[d]; r /= z.ext[d]; }
+        base[off] = T{};
+    }
+}
+int tnb_launch_zero_strided(tnb_ctx* ctx, int dtype, void* base, int rank, const int64_t* ext, const int64_t* stride) {
+    if (rank < 0 || rank > TNB_MAX_RANK) return tnb_set_error(ctx, TNB_EUNSUPPORTED, "zero fill: rank %d", rank);
+    ZeroArgs z;
+    z.rank = rank; z.total = 1;
+    for (int d = 0; d < rank; d++) { z.ext[d] = ext[d]; z.stride[d] = stride[d]; z.total *= ext[d]; }
+    int64_t blocks = (z.total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    switch (tnb_dtype_size(dtype)) {
+        case 16: zero_strided_kernel<double2><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double2*)base, z); break;
+        case 8: zero_strided_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>((double*)base, z); break;
+        case 4: zero_strided_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)base, z); break;
+        default: return tnb_set_error(ctx, TNB_EUNSUPPORTED, "zero fill: dtype %d", dtype);
+    }
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;

@@ -103,6 +103,7 @@ struct tnb_ctx {
     int sm_count = 148;
     int c64_mode = TNB_C64_TF32X3;
     int force_generic = 0;
+    int gemm_pair = 1;       // c64 GEMM steps on CTA pairs (TNB_OPT_GEMM_PAIR; env TNB_GEMM_PAIR=0 sets the default off)
     int last_kernel = -1;    // kernel id chosen by the most recent tnb_binary_einsum (introspection)
     // comm
     NcclApi* nccl = nullptr;
@@ -143,6 +144,7 @@ int tnb_launch_einsum_thin(tnb_ctx* ctx, int dtype, const EinsumArgs& args);
 int tnb_choose_kred(const tnb_ctx* ctx, int dtype, int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor,
                     int64_t* kchunk, int64_t* ws_elems);
 int tnb_launch_einsum_kred(tnb_ctx* ctx, int dtype, const EinsumArgs& args);   // -1: operands not 16-byte aligned
+int tnb_launch_zero_strided(tnb_ctx* ctx, int dtype, void* base, int rank, const int64_t* ext, const int64_t* stride);
 // kernels_c64_tc.cu
 int tnb_tc_c64_tile(int64_t M, int64_t N, int64_t K, int64_t L, bool a_mmajor, bool b_nmajor);
 int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, int64_t ldb, bool chunked);

@@ -42,9 +42,16 @@ def init_comm(ctx, rank: Optional[int] = None, world: Optional[int] = None):
     ctx.comm_init(box[0], rank, world)
 
 
-def allreduce_sum(ctx, array):
-    """In-place sum of a dense B200Array over all ranks (stream-ordered)."""
-    from ._lib import check
+def allreduce_sum(ctx, array, world: Optional[int] = None):
+    """In-place sum of a dense B200Array over all ranks (stream-ordered).  `world`: the rank count the caller's
+    launcher reports; a context whose communicator has a different size (init_comm never ran on it, or ran on
+    another context) would silently hand back a PARTIAL sum, so that is an error."""
+    from ._lib import check, TnbError, TNB_ENCCL
+    if world is not None and world > 1:
+        have = int(ctx.lib.tnb_comm_size(ctx.handle))
+        if have != world:
+            raise TnbError(TNB_ENCCL, f"all-reduce over {world} ranks requested but this context's communicator has "
+                                      f"{have} rank(s): call distributed.init_comm(ctx) first")
     check(ctx.handle, ctx.lib.tnb_comm_allreduce_sum(ctx.handle, array.buffer.handle,
                                                      array.offset * array.dtype.itemsize, array.size, array.dtype_code))
 
@@ -56,7 +63,7 @@ def contract_distributed(plan, ctx, limit: Optional[int] = None, reduce: bool = 
     plan.zero_output()
     plan.execute(b, s, e, accumulate=True)
     if reduce and world > 1:
-        allreduce_sum(ctx, plan.out_array)
+        allreduce_sum(ctx, plan.out_array, world)
     return plan.result()
 
 

@@ -38,6 +38,29 @@ def test_tc_matches_oracle(ctx, M, N, K):
     assert err < 20 * max(err2, 1e-7), f"3xTF32 error {err:.2e} vs FP32-SIMT error {err2:.2e}"
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 256, 256), (256, 128, 40), (384, 512, 200), (2500, 1300, 72), (258, 130, 2050),
+                                   (4096, 1024, 264), (1024, 256, 8192), (640, 64, 136), (8192, 4096, 128)])
+def test_pair_kernel_bit_identical_to_single_cta(ctx, M, N, K):
+    """The CTA-pair GEMM kernel (cta_group::2, dedicated drain warps) issues the same MMAs per output element in the
+    same order and chunks K the same way as the 1-CTA kernel: results must agree bit for bit (ragged edges, split-K,
+    conj, beta = 1 accumulation included)."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    a, b = crand(rng, (M, K)), crand(rng, (N, K))
+    ta, tb_ = tb.Tensor(a, ("m", "k")).conj(), tb.Tensor(b, ("n", "k"))
+    out = {}
+    for pair in (0, 1):
+        ctx.set_option(tb._lib.TNB_OPT_GEMM_PAIR, pair)
+        try:
+            out[pair] = tb.binary_einsum(ta, tb_).parent.copy()
+            assert ctx.last_kernel == "c64_tf32x3"
+        finally:
+            ctx.set_option(tb._lib.TNB_OPT_GEMM_PAIR, 1)
+    ref = np.conj(a).astype(np.complex128) @ b.astype(np.complex128).T
+    assert np.abs(out[1] - ref).max() / np.abs(ref).max() < 2e-5
+    assert np.array_equal(out[0], out[1]), f"max diff {np.abs(out[0] - out[1]).max():.3e}"
+
+
 def test_tc_conj_swap_and_scatter(ctx):
     """conj flags, operand swap (M not a multiple of 128 but N is), multi-mode free/contracted groups, custom
     output order (scattered epilogue)."""
