@@ -6,23 +6,48 @@
 A "step" contracts one batch of slices of the workload's network along its committed path
 (bench_paths/<workload>.json): `slices_per_step` slices on every GPU, dealt round-robin (slice id mod N), summed
 into the per-GPU accumulator, followed by the single all-reduce when N > 1.  Work per GPU is fixed as N grows
-("weak"): the full 2^k-slice amplitude is far beyond a benchmark's time budget, so each step samples a different
-window of the slice space.
+("weak") in the timed steps; after them the FULL amplitude (all 2^k slices over the N GPUs, hoisted steps on every
+GPU, one all-reduce) is contracted once and reported as `full_amplitude_s` — the strong-scaling figure — together
+with the amplitude and its distance from the committed single-GPU golden (tests/golden/sycamore53_m14_amplitude.json).
 
-Printed JSON (one line, rank 0): the driver contract keys plus `roofline` (dominant kernel, algorithmic flops or
-bytes per launch / CUDA-event duration measured on the context stream inside the timed region), `cpu_baseline`
-(the numpy/OpenBLAS oracle timed on the host cores on a bounded sub-slice) and `e2e` (same metric through the
-public API with the leaves coming from pinned host memory and the result read back, every step).
+Printed JSON (one line, rank 0): the driver contract keys plus
+  `roofline`      dominant kernel: algorithmic flops or bytes per launch / CUDA-event duration, measured in a separate
+                  profiled region (per-step events cost one host sync per slice, so `value` is timed WITHOUT them);
+  `cpu_baseline`  the numpy/OpenBLAS oracle timed on the host cores on a bounded sample (cores and BLAS threads stated);
+  `e2e`           same metric through the public API, leaves from pinned host memory, result read back, every step;
+  `configs`       (N = 1 only) one short measurement of each other BASELINE config with its own roofline / cpu_baseline.
 """
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+
+def _early_reference_setup():
+    """--impl reference: the BLAS thread pools are sized when numpy loads, and torch.distributed.run exports
+    OMP_NUM_THREADS=1 — so fix the environment BEFORE numpy is imported; ranks other than 0 have nothing to do."""
+    argv = sys.argv[1:]
+    ref = any(a == "--impl=reference" for a in argv) or any(
+        a == "--impl" and i + 1 < len(argv) and argv[i + 1] == "reference" for i, a in enumerate(argv))
+    if not ref:
+        return
+    if int(os.environ.get("RANK", "0")) != 0:
+        sys.exit(0)
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = str(n)
+
+
+_early_reference_setup()
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -40,10 +65,16 @@ WORKLOADS = {
     "mps_norm": "MPS <psi|psi>, 32 sites chi=128, complex128, zipper path (BASELINE configs[0])",
     "mps_mpo": "MPS-MPO <psi|H|psi>, 100 sites chi=1024, complex128, env sweep (BASELINE configs[4])",
 }
+EXTRA_CONFIGS = ["mps_norm", "regular3_n100_d4", "peps6x6_d4_boundary", "mps_mpo"]
+# measured on this pool's B200s with tools/yardstick.py (cuBLAS ZGEMM 8192^3, never linked into the product;
+# profiles/r1_summary.md): the FP64 "complex tensor-core peak" SURVEY §8d asks the c128 fraction to be quoted against
+ZGEMM_MEASURED_TFLOPS = 37.0
+GOLDEN_AMPLITUDE = os.path.join(ROOT, "tests", "golden", "sycamore53_m14_amplitude.json")
+C64_AMPLITUDE_BOUND = 5e-5        # the one stated c64 bound: relative to |amplitude|
 
 
 def build_workload(tb, name, path_file=""):
-    """-> (TensorNetwork, ContractionPath, dtype)"""
+    """-> (TensorNetwork, ContractionPath)"""
     from tools.make_paths import network  # noqa
     if name == "peps6x6_d4_boundary":
         tn, _ = tb.workloads.peps_norm_network(6, 6, D=4, p=2, dtype=np.complex128, seed=4)
@@ -111,6 +142,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """(cores this process may run on, BLAS threads numpy's BLAS will use)"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    blas = None
+    try:
+        from threadpoolctl import threadpool_info
+        th = [p.get("num_threads") for p in threadpool_info() if p.get("user_api") == "blas"]
+        blas = max(th) if th else None
+    except Exception:
+        pass
+    return cores, blas
+
+
 def subslice_path(tb, tn, path, budget_macs_log2=38.5):
     """The committed path with extra sliced indices, added until one sub-slice costs <= 2^budget MACs: the piece of
     the full-size workload a CPU can finish (also used by tests/test_gpu_zz_fullsize.py as the oracle-sized case)."""
@@ -124,23 +171,300 @@ def subslice_path(tb, tn, path, budget_macs_log2=38.5):
     return p
 
 
-def cpu_sample(tb, tn, path, budget_macs_log2=38.5):
-    """A bounded CPU sample of the same workload: slice further until one sub-slice is ~2^budget MACs, then time
-    the oracle on sub-slice 0.  Returns (flops, seconds, description)."""
+def cpu_sample(tb, tn, path, budget_macs_log2=38.5, deadline_s=40.0):
+    """A bounded CPU sample of the same workload.  Sliced paths: slice further until one sub-slice is ~2^budget
+    MACs, then time the oracle on sub-slice 0.  Un-sliced paths that are too long for the budget: the oracle walks
+    the same path step by step and stops at the first step boundary after `deadline_s` (rate = MACs done / time).
+    Returns (flops, seconds, description)."""
     from oracle import einsum_oracle as orc
     inputs = [t.inds for t in tn.tensors]
-    p = subslice_path(tb, tn, path, budget_macs_log2)
     arrays = [t.parent for t in tn.tensors]
+    cplx = np.iscomplexobj(arrays[0])
+    unit = 8.0 if cplx else 2.0
+    if len(path.sliced) == 0 and path.log2_macs > budget_macs_log2 + 1.0:
+        return cpu_sample_prefix(orc, arrays, inputs, path, unit, deadline_s)
+    p = subslice_path(tb, tn, path, budget_macs_log2)
     sl = list(p.sliced)
     t0 = time.perf_counter()
     orc.contract_sliced(arrays, inputs, p.steps, sl, slice_ids=[0])
     dt = time.perf_counter() - t0
-    cplx = np.iscomplexobj(arrays[0])
-    flops = (8.0 if cplx else 2.0) * 2.0 ** p.log2_macs
+    flops = unit * 2.0 ** p.log2_macs
     extra = len(p.sliced) - len(path.sliced)
-    desc = (f"1 sub-slice (slice 0 with {extra} extra sliced indices, 2^{p.log2_macs:.1f} MACs, peak 2^{p.log2_max_size:.0f} "
-            f"elements) of the same path; numpy/OpenBLAS permute->reshape->gemm restatement")
-    return flops, dt, desc
+    what = (f"1 sub-slice (slice 0 with {extra} extra sliced indices, 2^{p.log2_macs:.1f} MACs, peak 2^{p.log2_max_size:.0f} "
+            f"elements) of the same path") if extra or len(path.sliced) else f"the whole path (2^{p.log2_macs:.1f} MACs)"
+    return flops, dt, what + "; numpy/OpenBLAS permute->reshape->gemm restatement"
+
+
+def cpu_sample_prefix(orc, arrays, inds, path, unit, deadline_s):
+    """oracle.contract_path step by step with a wall-clock deadline (un-sliced, long paths: configs[4])."""
+    n = len(arrays)
+    total = {}
+    for t in inds:
+        for i in t:
+            total[i] = total.get(i, 0) + 1
+    vals = [np.asarray(a) for a in arrays]
+    vinds = [tuple(t) for t in inds]
+    cnt = [{i: 1 for i in t} for t in inds]
+    ext = {}
+    for a, t in zip(arrays, inds):
+        for ax, i in enumerate(t):
+            ext[i] = a.shape[ax]
+    macs, done = 0.0, 0
+    t0 = time.perf_counter()
+    for s, (i, j) in enumerate(path.steps):
+        ci = dict(cnt[i])
+        for k, v in cnt[j].items():
+            ci[k] = ci.get(k, 0) + v
+        dims = [k for k, v in ci.items() if v == total[k]]
+        c, c_inds = orc.binary_einsum(vals[i], vinds[i], vals[j], vinds[j], dims=dims)
+        macs += float(np.prod([float(ext[k]) for k in ci]))
+        vals.append(c); vinds.append(c_inds)
+        cnt.append({k: v for k, v in ci.items() if v < total[k]})
+        vals[i] = vals[j] = None
+        done = s + 1
+        if time.perf_counter() - t0 > deadline_s:
+            break
+    dt = time.perf_counter() - t0
+    return unit * macs, dt, (f"the first {done} of {len(path.steps)} pairwise steps of the same path (2^{np.log2(max(macs, 1)):.1f} of "
+                             f"2^{path.log2_macs:.1f} MACs, stopped at the first step boundary after {deadline_s:.0f} s); "
+                             f"numpy/OpenBLAS permute->reshape->gemm restatement")
+
+
+def load_peaks():
+    peaks = {}
+    pk_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_file):
+        peaks = json.load(open(pk_file))
+    return peaks
+
+
+def roofline_of(plan, step_times, dtype, workload):
+    """roofline object of the kernel with the largest share of the profiled region + the per-step rows"""
+    peaks = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    by_kernel, rows = {}, []
+    for s in range(plan.nsteps):
+        si = plan.step_info(s)
+        t_ms, runs = step_times[s]
+        if runs == 0:
+            continue
+        k = by_kernel.setdefault(si["kernel_name"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        k["ms"] += t_ms; k["flops"] += si["flops"] * runs; k["bytes"] += si["bytes"] * runs; k["launches"] += runs
+        rows.append({"step": s, **{x: si[x] for x in ("M", "N", "K", "L", "kernel_name", "flops", "bytes")},
+                     "ms_avg": t_ms / runs, "runs": runs})
+    if not by_kernel:
+        return None, rows
+    name, k = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
+    ai = k["flops"] / max(k["bytes"], 1.0)
+    # c64: a complex MAC is 4 real MACs, each needing 3 TF32 products for fp32-grade accuracy -> the tensor peak in
+    # "8 flops per complex MAC" units is tf32_dense / 3, tf32_dense = bf16_dense / 2.  c128: tcgen05 has no FP64 kind;
+    # the FP64 peak is the cuBLAS ZGEMM measured on this pool (SURVEY §8d: "% of measured cublasZgemm").
+    if dtype == np.complex64 or dtype == np.float32:
+        tpeak, basis = bf16_peak / 2.0 / 3.0, "bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split); " + peak_src
+    else:
+        tpeak, basis = ZGEMM_MEASURED_TFLOPS, "cuBLAS ZGEMM 8192^3 measured on this pool (tools/yardstick.py, profiles/r1_summary.md)"
+    ridge = tpeak * 1e12 / (hbm_peak * 1e9)
+    if ai >= ridge:
+        ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": None, "peak_basis": basis}
+    else:
+        ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "peak_basis": peak_src}
+    # DRAM traffic of the dominant kernel: from the ncu --set full capture of THIS build (the file records the digest of
+    # the kernel sources it was taken from; a capture of other sources is reported as stale, not silently reused)
+    tr_file = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tr_file):
+        trj = json.load(open(tr_file))
+        tr = trj.get("workloads", {}).get(workload, {}).get(name)
+        if tr:
+            cur = None
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("_tnb_build", os.path.join(ROOT, "tenet.jl_b200", "build.py"))
+                mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+                cur = mod.source_digest()
+            except Exception:
+                pass
+            if cur is not None and cur == trj.get("source_digest"):
+                roofline["traffic"] = tr["dram_bytes"]
+                roofline["traffic_note"] = (f"ncu dram read+write of the largest launch of this kernel, {tr['launch']}: "
+                                            f"{tr['ratio']:.3f} x its algorithmic bytes (profiles/r2_traffic.json, same sources)")
+            else:
+                roofline["traffic_note"] = "profiles/r2_traffic.json was captured from other kernel sources: stale, not reported"
+    roofline.update({"kernel": name, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"],
+                     "share_of_step": k["ms"] / max(sum(v["ms"] for v in by_kernel.values()), 1e-9),
+                     "arithmetic_intensity": ai,
+                     "kernels": {n: {"ms": v["ms"], "tflops": v["flops"] / max(v["ms"], 1e-9) / 1e9,
+                                     "gbs": v["bytes"] / max(v["ms"], 1e-9) / 1e6, "launches": v["launches"]}
+                                 for n, v in by_kernel.items()}})
+    return roofline, rows
+
+
+class Runner:
+    """One workload on this rank's GPU: plan, pinned leaves, step function, timed regions."""
+
+    def __init__(self, tb, torch, dist, ctx, stream, name, rank, world, path_file="", slices_per_step=0):
+        self.tb, self.torch, self.dist, self.ctx, self.stream = tb, torch, dist, ctx, stream
+        self.name, self.rank, self.world = name, rank, world
+        self.tn, self.path = build_workload(tb, name, path_file)
+        tn = self.tn
+        self.dtype = tb.tensor._promote_dtype(*[t.dtype for t in tn.tensors])
+        self.cplx = self.dtype.kind == "c"
+        dtype, cplx = self.dtype, self.cplx
+        # pinned host copies of the leaves (e2e: uploaded every step) + device residency (value: resident)
+        self.pinned = []
+        for t in tn.tensors:
+            h = np.asfortranarray(t.parent.astype(dtype))
+            flat = np.ascontiguousarray(h.reshape(-1, order="F"))
+            real = flat.view(np.float32 if dtype.itemsize // (2 if cplx else 1) == 4 else np.float64)
+            self.pinned.append(torch.from_numpy(real.copy()).pin_memory())
+        self.plan = tb.ContractionPlan(tn, self.path, ctx=ctx)
+        self.info = self.plan.info
+        self.nslices = self.plan.nslices
+        self.flops_slice = self.info["flops_per_slice"]
+        S = slices_per_step
+        if S <= 0:
+            S = max(1, int(15e12 / max(self.flops_slice, 1.0)))      # first guess, refined by calibrate()
+        self.S = max(1, min(S, max(1, self.nslices // max(world, 1))))
+        self.auto_S = slices_per_step <= 0
+        self.replicas = self.nslices == 1   # un-sliced network: nothing to shard -> N independent replicas, no collective
+
+    def step_range(self, i):
+        if self.replicas:
+            return 0, 1, 1
+        base = (i * self.world * self.S) % max(self.nslices - self.world * self.S + 1, 1)
+        return base + self.rank, self.world, base + self.world * self.S
+
+    def run_step(self, i, e2e):
+        tb, ctx, plan = self.tb, self.ctx, self.plan
+        if e2e:
+            for t, buf in zip(self.tn.tensors, self.pinned):
+                arr = t._dev
+                tb._lib.check(ctx.handle, ctx.lib.tnb_upload(ctx.handle, arr.buffer.handle, 0, buf.data_ptr(),
+                                                             arr.size * self.dtype.itemsize))
+        plan.zero_output()
+        b, s, e = self.step_range(i)
+        plan.execute(b, s, e, accumulate=True)
+        if self.world > 1 and not self.replicas:
+            tb.distributed.allreduce_sum(ctx, plan.out_array, self.world)
+        if e2e:
+            return plan.out_array.to_numpy()
+        return None
+
+    def barrier(self):
+        self.ctx.sync()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def calibrate(self):
+        """the very first step pays one-time costs (function attributes, NCCL communicator set-up inside the first
+        all-reduce): run it once untimed, then size S for ~1 s steps from a second one"""
+        torch = self.torch
+        self.run_step(0, False)
+        self.barrier()
+        t0 = time.perf_counter()
+        self.run_step(0, False)
+        self.ctx.sync()
+        first = time.perf_counter() - t0
+        if self.auto_S and self.nslices > 1:
+            per_slice = first / self.S
+            S2 = max(1, min(int(round(1.0 / max(per_slice, 1e-6))), 4096, max(1, self.nslices // max(self.world, 1))))
+            if self.world > 1:
+                t = torch.tensor([S2], device="cuda")
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+                S2 = int(t.item())
+            self.S = S2
+        return first
+
+    def timed(self, first_step, nsteps, e2e):
+        """K steps bracketed by barrier + sync on both sides, CUDA events on the context stream -> (ms, last result)"""
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        with torch.cuda.stream(self.stream):
+            ev0.record()
+        res = None
+        for i in range(nsteps):
+            res = self.run_step(first_step + i, e2e)
+        with torch.cuda.stream(self.stream):
+            ev1.record()
+        self.barrier()
+        return ev0.elapsed_time(ev1), res
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def work(self, nsteps):
+        total_slices = nsteps * self.world * self.S if not self.replicas else nsteps * self.world
+        hoisted = self.info["flops_hoisted"] * nsteps * self.world
+        return total_slices, total_slices * self.flops_slice + hoisted
+
+    def full_amplitude(self):
+        """ALL slices over the N GPUs (slice s on rank s mod N, hoisted steps on every rank, one all-reduce):
+        the strong-scaling measurement.  -> (seconds, result array)"""
+        torch, plan = self.torch, self.plan
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        with torch.cuda.stream(self.stream):
+            ev0.record()
+        plan.zero_output()
+        plan.execute(self.rank, self.world, self.nslices, accumulate=True)
+        if self.world > 1:
+            self.tb.distributed.allreduce_sum(self.ctx, plan.out_array, self.world)
+        with torch.cuda.stream(self.stream):
+            ev1.record()
+        self.barrier()
+        (ms,) = self.max_over_ranks(ev0.elapsed_time(ev1))
+        return ms * 1e-3, plan.out_array.to_numpy()
+
+    def close(self):
+        self.plan.close()
+        for t in self.tn.tensors:
+            t._dev = None
+        self.pinned = []
+
+
+def dtype_name(dtype):
+    return {"complex64": "c64", "complex128": "c128"}.get(str(dtype), str(dtype))
+
+
+def measure_extra(tb, torch, ctx, stream, name, no_cpu):
+    """A short single-GPU measurement of another BASELINE config: 2 warm-up + 2 timed steps, a profiled step for the
+    roofline, a bounded CPU sample."""
+    t_start = time.perf_counter()
+    r = Runner(tb, torch, None, ctx, stream, name, 0, 1)
+    r.calibrate()
+    r.run_step(1, False)
+    ms, _ = r.timed(2, 2, False)
+    ms_e2e, res = r.timed(2, 2, True)
+    r.plan.profile(True)
+    r.run_step(2, False)
+    ctx.sync()
+    st = r.plan.step_times()
+    r.plan.profile(False)
+    roofline, _ = roofline_of(r.plan, st, r.dtype, name)
+    slices, flops = r.work(2)
+    out = {"description": WORKLOADS[name], "dtype": dtype_name(r.dtype), "value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+           "ms_per_step": ms / 2, "e2e": flops / (ms_e2e * 1e-3) / 1e12, "slices_per_step": r.S if not r.replicas else None,
+           "nslices_total": r.nslices, "flops_per_slice": r.flops_slice, "steps_per_contraction": r.info["nsteps_per_slice"] + r.info["nsteps_hoisted"],
+           "result": [float(np.real(res).sum()), float(np.imag(res).sum())], "roofline": roofline}
+    if not no_cpu:
+        cores, blas = host_threads()
+        fl, dt, desc = cpu_sample(tb, r.tn, r.path, budget_macs_log2=36.5, deadline_s=12.0)
+        out["cpu_baseline"] = {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "blas_threads": blas, "kind": "port",
+                               "sample": desc, "seconds": dt}
+    r.close()
+    ctx.trim()
+    out["wall_s"] = time.perf_counter() - t_start
+    return out
 
 
 def main():
@@ -152,6 +476,8 @@ def main():
     ap.add_argument("--workload", default="sycamore53_m14")
     ap.add_argument("--slices-per-step", type=int, default=0, help="per GPU; 0 = sized for ~1 s steps")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other BASELINE configs (N = 1)")
+    ap.add_argument("--no-full", action="store_true", help="skip the full-amplitude (strong scaling) run")
     ap.add_argument("--c64-mode", default="auto", choices=["auto", "simt", "tf32x3", "tf32x3_fast"])
     ap.add_argument("--dump-steps", default="")
     ap.add_argument("--path-file", default="", help="candidate path JSON to use instead of bench_paths/<workload>.json")
@@ -163,25 +489,24 @@ def main():
     if world != a.gpus and world > 1:
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
 
-    import __graft_entry__ as g
-    g.build()
-    import tenet_jl_b200 as tb
-
-    tn, path = build_workload(tb, a.workload, a.path_file)
-    dtype = tb.tensor._promote_dtype(*[t.dtype for t in tn.tensors])
-    cplx = dtype.kind == "c"
-    flops_unit = 8.0 if cplx else 2.0
-    ncores = os.cpu_count() or 1
-
     # ------------------------------------------------------------------------------------------------
     if a.impl == "reference":
-        # the reference's CPU algorithm (numpy/OpenBLAS restatement: the reference itself cannot run here, see
-        # BASELINE.md §2) on the host cores, rank 0 only.
-        if rank != 0:
-            return
+        # The reference's CPU algorithm (numpy/OpenBLAS restatement: the reference itself cannot run here, BASELINE.md
+        # §2) on the host cores, rank 0 only (the other ranks left in _early_reference_setup).  libtnb200.so is never
+        # loaded in this process: only the pure-Python workload / path modules of the package are imported.
+        import tenet_jl_b200 as tb
+        tn, path = build_workload(tb, a.workload, a.path_file)
+        dtype = tb.tensor._promote_dtype(*[t.dtype for t in tn.tensors])
+        cores, blas = host_threads()
+        # size the per-step sample so that the whole --steps/--warmup run stays within ~3 minutes
+        fl, dt, desc = cpu_sample(tb, tn, path, budget_macs_log2=36.0, deadline_s=6.0)
+        rate = fl / dt
+        per_step_s = max(4.0, min(20.0, 150.0 / max(a.steps + a.warmup, 1)))
+        unit = 8.0 if dtype.kind == "c" else 2.0
+        budget = float(np.log2(max(rate * per_step_s / unit, 2.0 ** 30)))
         vals = []
         for i in range(a.warmup + a.steps):
-            fl, dt, desc = cpu_sample(tb, tn, path)
+            fl, dt, desc = cpu_sample(tb, tn, path, budget_macs_log2=budget, deadline_s=per_step_s)
             if i >= a.warmup:
                 vals.append((fl, dt))
         fl = sum(v[0] for v in vals)
@@ -190,14 +515,17 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": "contraction_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / max(a.steps, 1) * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "c64" if dtype == np.complex64 else str(dtype),
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(dtype),
             "data": "synthetic", "config": {"workload": a.workload, "description": WORKLOADS[a.workload]},
-            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": ncores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "blas_threads": blas, "kind": "port", "sample": desc},
             "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
 
     # ------------------------------------------------------------------------------------------------
+    import __graft_entry__ as g
+    g.build()
+    import tenet_jl_b200 as tb
     import torch
     torch.cuda.set_device(local_rank)
     dist = None
@@ -211,199 +539,99 @@ def main():
         tb.distributed.init_comm(ctx, rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
-    # pinned host copies of the leaves (e2e: uploaded every step) + device residency (value: resident)
-    pinned = []
-    for t in tn.tensors:
-        h = np.asfortranarray(t.parent.astype(dtype))
-        flat = np.ascontiguousarray(h.reshape(-1, order="F"))
-        real = flat.view(np.float32 if dtype.itemsize // (2 if cplx else 1) == 4 else np.float64)
-        pinned.append(torch.from_numpy(real.copy()).pin_memory())
-    plan = tb.ContractionPlan(tn, path, ctx=ctx)
-    info = plan.info
-    nslices = plan.nslices
-    flops_slice = info["flops_per_slice"]
-    S = a.slices_per_step
-    if S <= 0:
-        # ~1 s per step assuming ~15 TFLOP/s for a first guess; refined from the warm-up below
-        S = max(1, int(15e12 / max(flops_slice, 1.0)))
-    S = max(1, min(S, max(1, nslices // max(world, 1))))
-
-    replicas = nslices == 1       # un-sliced network: nothing to shard -> N independent replicas, no collective
-
-    def step_range(i):
-        if replicas:
-            return 0, 1, 1
-        base = (i * world * S) % max(nslices - world * S + 1, 1)
-        return base + rank, world, base + world * S
-
-    def run_step(i, e2e):
-        if e2e:
-            for t, buf in zip(tn.tensors, pinned):
-                arr = t._dev
-                tb._lib.check(ctx.handle, ctx.lib.tnb_upload(ctx.handle, arr.buffer.handle, 0, buf.data_ptr(),
-                                                             arr.size * dtype.itemsize))
-        plan.zero_output()
-        b, s, e = step_range(i)
-        plan.execute(b, s, e, accumulate=True)
-        if world > 1 and not replicas:
-            tb.distributed.allreduce_sum(ctx, plan.out_array)
-        if e2e:
-            return plan.out_array.to_numpy()
-        return None
-
-    def barrier():
-        ctx.sync()
-        if world > 1:
-            dist.barrier()
-
-    # warm-up (also calibrates S when auto): the very first step pays one-time costs (function attributes, NCCL
-    # communicator set-up inside the first all-reduce), so it is run once untimed before the calibration step
-    run_step(0, False)
-    barrier()
-    t0 = time.perf_counter()
-    run_step(0, False)
-    ctx.sync()
-    first = time.perf_counter() - t0
-    if a.slices_per_step <= 0 and nslices > 1:
-        per_slice = first / S
-        S2 = max(1, min(int(round(1.0 / max(per_slice, 1e-6))), 4096, max(1, nslices // max(world, 1))))
-        if world > 1:
-            t = torch.tensor([S2], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            S2 = int(t.item())
-        S = S2
+    r = Runner(tb, torch, dist, ctx, stream, a.workload, rank, world, a.path_file, a.slices_per_step)
+    dtype = r.dtype
+    r.calibrate()
     for i in range(1, a.warmup):
-        run_step(i, False)
-    barrier()
+        r.run_step(i, False)
+    r.barrier()
 
-    # timed region 1: inputs resident in HBM
+    # timed region 1: inputs resident in HBM, no per-step events
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    plan.profile(True)
     l0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        ev0.record()
-    for i in range(a.steps):
-        run_step(a.warmup + i, False)
-    with torch.cuda.stream(stream):
-        ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms, _ = r.timed(a.warmup, a.steps, False)
     launches = ctx.launch_count - l0
-    step_times = plan.step_times()
-    plan.profile(False)
-
     # timed region 2: end to end (pinned host leaves -> H2D every step, result D2H every step)
-    barrier()
-    with torch.cuda.stream(stream):
-        ev0.record()
-    res = None
-    for i in range(a.steps):
-        res = run_step(a.warmup + i, True)
-    with torch.cuda.stream(stream):
-        ev1.record()
-    barrier()
-    ms_e2e = ev0.elapsed_time(ev1)
+    ms_e2e, res = r.timed(a.warmup, a.steps, True)
     clocks = sampler.stop() if sampler else None
+    ms, ms_e2e = r.max_over_ranks(ms, ms_e2e)
+    # region 3 (not part of any reported throughput): one step with per-step CUDA events -> kernel shares / roofline
+    r.plan.profile(True)
+    r.run_step(a.warmup, False)
+    ctx.sync()
+    step_times = r.plan.step_times()
+    r.plan.profile(False)
+    r.barrier()
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    # strong scaling: the whole amplitude over the N GPUs
+    full = None
+    if not a.no_full and not r.replicas:
+        secs, amp = r.full_amplitude()
+        z = complex(np.asarray(amp).reshape(-1)[0]) if amp.size == 1 else None
+        full = {"seconds": secs, "nslices": r.nslices, "slices_per_gpu": -(-r.nslices // world),
+                "tflops": (r.nslices * r.flops_slice + world * r.info["flops_hoisted"]) / secs / 1e12}
+        if z is not None:
+            full["amplitude"] = [z.real, z.imag]
+            if a.workload == "sycamore53_m14" and not a.path_file and os.path.exists(GOLDEN_AMPLITUDE):
+                gold = json.load(open(GOLDEN_AMPLITUDE))
+                g0 = complex(*gold["amplitude_c64_n1"])
+                rel = abs(z - g0) / abs(g0)
+                full["rel_diff_vs_golden_n1"] = rel
+                full["bound"] = C64_AMPLITUDE_BOUND
+                full["within_bound"] = bool(rel <= C64_AMPLITUDE_BOUND)
 
-    total_slices = a.steps * world * S
-    hoisted = info["flops_hoisted"] * a.steps * world
-    total_flops = total_slices * flops_slice + hoisted
+    total_slices, total_flops = r.work(a.steps)
     value = total_flops / (ms * 1e-3) / 1e12
     e2e_value = total_flops / (ms_e2e * 1e-3) / 1e12
-    h2d = int(sum(t._dev.size for t in tn.tensors) * dtype.itemsize)
-    d2h = int(plan.out_array.size * dtype.itemsize)
+    h2d = int(sum(t._dev.size for t in r.tn.tensors) * dtype.itemsize)
+    d2h = int(r.plan.out_array.size * dtype.itemsize)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel (by measured time) ------------------------------------------------
-    peaks = {}
-    pk_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk_file):
-        peaks = json.load(open(pk_file))
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    by_kernel = {}
-    rows = []
-    for s in range(plan.nsteps):
-        si = plan.step_info(s)
-        t_ms, runs = step_times[s]
-        if runs == 0:
-            continue
-        k = by_kernel.setdefault(si["kernel_name"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-        k["ms"] += t_ms; k["flops"] += si["flops"] * runs; k["bytes"] += si["bytes"] * runs; k["launches"] += runs
-        rows.append({"step": s, **{x: si[x] for x in ("M", "N", "K", "L", "kernel_name", "flops", "bytes")},
-                     "ms_avg": t_ms / runs, "runs": runs})
-    roofline = None
-    if by_kernel:
-        name, k = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
-        ai = k["flops"] / max(k["bytes"], 1.0)
-        # c64: a complex MAC is 4 real MACs, each needing 3 TF32 products for fp32-grade accuracy -> the tensor
-        # peak in "8 flops per complex MAC" units is tf32_dense / 3, tf32_dense = bf16_dense / 2.  c128: no FP64
-        # tcgen05 kind exists; DMMA/DFMA nominal 37 TFLOP/s (not in MEASURED_PEAKS).
-        if dtype == np.complex64 or dtype == np.float32:
-            tpeak, basis = bf16_peak / 2.0 / 3.0, "bf16_tflops_sustained/2 (TF32) /3 (3xTF32 split)"
-        else:
-            tpeak, basis = 37.0, "nominal FP64 (148 SM x 64 FMA/clk x 1.965 GHz); no measured FP64 peak available"
-        ridge = tpeak * 1e12 / (hbm_peak * 1e9)
-        if ai >= ridge:
-            ach = k["flops"] / (k["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                        "traffic": None, "peak_basis": basis + "; " + peak_src}
-        else:
-            ach = k["bytes"] / (k["ms"] * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                        "traffic": None, "peak_basis": peak_src}
-        tr_file = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if a.workload == "sycamore53_m14" and os.path.exists(tr_file):
-            tr = json.load(open(tr_file)).get(name)
-            if tr:
-                roofline["traffic"] = tr["dram_bytes"]
-                roofline["traffic_note"] = (f"ncu dram read+write of the largest launch of this kernel, {tr['launch']}: "
-                                            f"{tr['ratio']:.3f} x its algorithmic bytes (profiles/r1_traffic.json)")
-        roofline.update({"kernel": name, "launches": k["launches"], "avg_launch_ms": k["ms"] / k["launches"],
-                         "share_of_step": k["ms"] / max(sum(v["ms"] for v in by_kernel.values()), 1e-9),
-                         "arithmetic_intensity": ai,
-                         "kernels": {n: {"ms": v["ms"], "tflops": v["flops"] / max(v["ms"], 1e-9) / 1e9,
-                                         "gbs": v["bytes"] / max(v["ms"], 1e-9) / 1e6, "launches": v["launches"]}
-                                     for n, v in by_kernel.items()}})
+    roofline, rows = roofline_of(r.plan, step_times, dtype, a.workload)
     if a.dump_steps:
         os.makedirs(os.path.dirname(os.path.abspath(a.dump_steps)), exist_ok=True)
         json.dump(rows, open(a.dump_steps, "w"))
 
     cpu = None
     if world == 1 and not a.no_cpu:
-        fl, dt, desc = cpu_sample(tb, tn, path)
-        cpu = {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": ncores, "kind": "port", "sample": desc,
+        cores, blas = host_threads()
+        fl, dt, desc = cpu_sample(tb, r.tn, r.path)
+        cpu = {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "blas_threads": blas, "kind": "port", "sample": desc,
                "seconds": dt}
 
+    info = r.info
     out = {
         "metric": "contraction_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"complex64": "c64", "complex128": "c128"}.get(str(dtype), str(dtype)),
+        "vs_baseline": None, "dtype": dtype_name(dtype),
         "data": "synthetic",
-        "config": {"workload": a.workload, "description": WORKLOADS[a.workload], "slices_per_step_per_gpu": S,
-                   "nslices_total_log2": float(np.log2(max(nslices, 1))), "flops_per_slice": flops_slice,
+        "config": {"workload": a.workload, "description": WORKLOADS[a.workload], "slices_per_step_per_gpu": r.S,
+                   "nslices_total_log2": float(np.log2(max(r.nslices, 1))), "flops_per_slice": r.flops_slice,
                    "steps_per_slice": info["nsteps_per_slice"], "peak_intermediate_bytes": info["max_intermediate_elems"] * dtype.itemsize,
                    "workspace_bytes": info["workspace_bytes"],
                    "l2": "intermediates (>= hundreds of MB per slice) exceed the 126 MB L2; no explicit flush",
                    "parallelism": ("single GPU" if world == 1 else f"{world} independent replicas (un-sliced network, no collective)"
-                                   if replicas else f"slices round-robin over {world} GPU(s), one all-reduce per step")},
+                                   if r.replicas else f"slices round-robin over {world} GPU(s), one all-reduce per step")},
         "slices_per_s": total_slices / (ms * 1e-3), "slices_per_s_per_gpu": total_slices / (ms * 1e-3) / world,
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / a.steps, "result_checksum": [float(np.real(res).sum()), float(np.imag(res).sum())] if res is not None else None},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "full_amplitude": full, "full_amplitude_s": full["seconds"] if full else None,
     }
+    if world == 1 and not a.no_extras and a.workload == "sycamore53_m14":
+        r.close()
+        ctx.trim()
+        cfgs = {}
+        for name in EXTRA_CONFIGS:
+            try:
+                cfgs[name] = measure_extra(tb, torch, ctx, stream, name, a.no_cpu)
+            except Exception as e:  # noqa: BLE001 — an extra must never cost the headline line
+                cfgs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        out["configs"] = cfgs
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

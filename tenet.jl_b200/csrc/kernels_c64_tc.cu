@@ -999,15 +999,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 pl[i] = __float_as_uint(rh); pl[8 + i] = __float_as_uint(re - rh);
                 pl[16 + i] = __float_as_uint(ih); pl[24 + i] = __float_as_uint(im - ih);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(raw_empty(rs));          // raw stage consumed (values are in registers)
             mbar_wait(apl_empty(ps), pphase ^ 1);
             tc_fence_after();
             tmem_st32(lane_base + ps * SK_APL_COLS, pl);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(apl_full(ps));
+            if (lane == 0) {
+                mbar_arrive(raw_empty(rs));                     // released after the tcgen05.st consumed the loaded values (an arrive
+                mbar_arrive(apl_full(ps));                      // right after the ld.shared does not wait for them to return)
+            }
         }
     } else if (warp < 16) {
         // ---- epilogue warps: TMEM -> (combine) -> staging (rank order) -> C (ascending addresses) ----
