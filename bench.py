@@ -427,8 +427,7 @@ class Runner:
 
     def close(self):
         self.plan.close()
-        for t in self.tn.tensors:
-            t._dev = None
+        self.plan = self.tn = None      # leaves are freed with their Tensor objects (stream-ordered allocator)
         self.pinned = []
 
 

@@ -188,6 +188,17 @@ int tnb_contract_path(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nleaves,
                       int64_t slice_begin, int64_t slice_step, int64_t slice_end,
                       const tnb_tensor* out);
 
+/* ---- multi-GPU, single process: tnb_contract_path over `ngpus` devices of this box -------------------------
+ * The reference calls `contract` from ONE Julia task, so this is the entry a drop-in `contract(tn; path,
+ * ngpus)` binds: leaves and `out` live on ctx's device; the library runs one host thread + one context per additional
+ * device (cached in ctx), broadcasts the leaves, deals slice s to rank s mod ngpus, sums the accumulators with one NCCL
+ * all-reduce and leaves the result in `out` (which must be a dense view).  ngpus = 1 is tnb_contract_path.
+ * Un-sliced paths do not shard (rank 0 contracts, the others contribute zeros). */
+int tnb_multi_contract_path(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nleaves,
+                            const int32_t* steps, int32_t nsteps,
+                            const int32_t* sliced_modes, int32_t nsliced,
+                            const tnb_tensor* out, int32_t ngpus);
+
 /* ---- multi-GPU: one process per GPU, slices dealt round-robin, one all-reduce at the end -------
  * (the reference has no distributed code: README.md:22 only advertises it.)
  * NCCL is dlopen'ed at run time; the 128-byte unique id is created on rank 0 and shipped to the

@@ -153,6 +153,15 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         t.alpha[0] = alpha[0]; t.alpha[1] = alpha[1]; t.beta[0] = beta[0]; t.beta[1] = beta[1];
         if (S.kernel == TNB_KERNEL_STEM) return tnb_launch_stem(ctx, dtype, t);
         const int64_t cnt = (int64_t)S.st_tm * S.st_ncol;
+        // 128-column passes with a DENSE small operand: all passes in one launch of the CTA-pair kernel (cta_group::2 MMAs,
+        // B tile by TMA) with the same sorted-pattern epilogue; otherwise (gathered small operand, misalignment,
+        // TNB_OPT_GEMM_PAIR = 0) the 1-CTA stem kernel below
+        if (S.st_ncol == 128 && S.st_tm == 128 && (sw ? S.a_mmajor : S.b_nmajor)) {
+            const int64_t Ns = sw ? S.M : S.N;
+            const int64_t ldb = S.K > 1 ? (sw ? S.ak.stride : S.bk.stride) : Ns;
+            int rc = tnb_launch_c64_pair_staged(ctx, t, Ns, ldb, S.st_rel_small);
+            if (rc != -1) return rc;
+        }
         for (int ps = 0; ps < S.st_npass; ps++) {
             t.N = S.st_ncol; t.n0 = ps * S.st_ncol;
             t.rel = dev_blob + S.st_rel_pos + ps * cnt; t.pos = dev_blob + S.st_pos_pos + ps * cnt;

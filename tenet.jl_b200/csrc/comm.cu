@@ -18,6 +18,7 @@ struct NcclApi {
     int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
     int (*CommInitRank)(void**, int, ncclUniqueId_t, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -40,6 +41,7 @@ static NcclApi* load_nccl(std::string* why) {
             api.GetUniqueId = (int (*)(ncclUniqueId_t*))dlsym(api.handle, "ncclGetUniqueId");
             api.CommInitRank = (int (*)(void**, int, ncclUniqueId_t, int))dlsym(api.handle, "ncclCommInitRank");
             api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclBroadcast");
             api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
             api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
             if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
@@ -51,6 +53,17 @@ static NcclApi* load_nccl(std::string* why) {
     }
     if (!api.handle) { if (why) *why = err.empty() ? "libnccl.so.2 not found" : err; return nullptr; }
     return &api;
+}
+
+// in-place broadcast of raw bytes from `root` (tnb_multi_contract_path ships the leaves to the other devices with it)
+int tnb_comm_broadcast_bytes(tnb_ctx* ctx, void* ptr, size_t bytes, int root) {
+    if (!ctx || !ctx->comm) return tnb_set_error(ctx, TNB_ENCCL, "communicator not initialised");
+    if (!ctx->nccl->Broadcast) return tnb_set_error(ctx, TNB_ENCCL, "libnccl lacks ncclBroadcast");
+    if (!bytes) return TNB_OK;
+    cudaSetDevice(ctx->device);
+    int r = ctx->nccl->Broadcast(ptr, ptr, bytes, 0 /* ncclInt8 */, root, ctx->comm, ctx->stream);
+    if (r) return tnb_set_error(ctx, TNB_ENCCL, "ncclBroadcast: %s", ctx->nccl->GetErrorString ? ctx->nccl->GetErrorString(r) : "error");
+    return TNB_OK;
 }
 
 extern "C" {

@@ -61,6 +61,7 @@ int tnb_ctx_destroy(tnb_ctx* ctx) {
     if (!ctx) return TNB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    tnb_multi_release(ctx);
     tnb_comm_destroy(ctx);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     ctx->free_blocks.clear();

@@ -177,6 +177,12 @@ struct TcArgs {
     // ws[(z*N + n)*M + m]; the deterministic reducer of kernels_generic.cu finishes the job
     float2* ws;
     uint32_t splitk, kb_per_split;
+    // pair kernel, STAGED epilogue (huge x small steps, stem tables of the planner): tile bases hi[M / 128], sorted tile
+    // pattern rel / its inverse pos per 128-column pass [N / 128][128 * 128]
+    const int64_t* st_hi;
+    const int64_t* st_rel;
+    const int64_t* st_pos;
+    int32_t st_run_shift, st_vec2, st_rel_small;   // log2 run length; 16-byte pairs allowed; every rel entry fits int32
 };
 
 __device__ __forceinline__ int64_t tabc(const TabRef& t, uint32_t i) {
@@ -774,6 +780,10 @@ int launch_tc_acc(tnb_ctx* ctx, const TcArgs& a) {
     return TNB_OK;
 }
 
+// bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks stay
+// conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
+__device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
+
 #include "pair_kernel.inc"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -884,9 +894,6 @@ __device__ __forceinline__ void split_store_b(uint8_t* kb_base, int plane_bytes,
     *reinterpret_cast<float4*>(kb_base + plane_bytes + off_im) = make_float4(il[0], il[1], il[2], il[3]);
 }
 
-// bank swizzle of staging indices: a permutation inside aligned 16-element groups (reads of consecutive ranks stay
-// conflict free, aligned pairs stay pairs) that spreads ranks which differ by a power-of-two stride over all banks
-__device__ __forceinline__ uint32_t sk_swz(uint32_t r) { return r ^ ((r >> 4) & 15u) ^ ((r >> 8) & 15u); }
 
 // BSTREAM: the small operand's planes do not fit in shared memory (N*K*16 > 64 KB): a tiny pre-pass
 // (stem_bsplit_kernel) splits it once into global memory in the UMMA plane layout and lane 8 of the copy warp
@@ -1334,6 +1341,8 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
     a.ws = (float2*)e.ws;
+    a.st_hi = a.st_rel = a.st_pos = nullptr;
+    a.st_run_shift = a.st_vec2 = a.st_rel_small = 0;
     a.splitk = e.splitk > 1 ? (uint32_t)e.splitk : 1u;
     a.kb_per_split = e.splitk > 1 ? (uint32_t)e.kchunk : (uint32_t)((e.K + TC_BK - 1) / TC_BK);
     if (!chunked && a.splitk == 1 && nt >= 128) {
@@ -1341,7 +1350,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
         return launch_tc<128>(ctx, a);
     }
     if (!tc_acc_ok(a)) return -1;
-    if (ctx->gemm_pair && a.M > (uint32_t)TC_BM) return launch_tc_pair(ctx, a);   // CTA pairs on 256 x 128 tiles
+    if (ctx->gemm_pair && a.M > (uint32_t)TC_BM) return launch_tc_pair<false>(ctx, a);   // CTA pairs on 256 x 128 tiles
     return launch_tc_acc(ctx, a);
 }
 
@@ -1402,4 +1411,29 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass)
     if (e.N <= 16) return launch_stem_tc<16, false>(ctx, a);
     if (e.N <= 32) return launch_stem_tc<32, false>(ctx, a);
     return stem_wide64() ? launch_stem_tc<64, false, true>(ctx, a) : launch_stem_tc<64, false>(ctx, a);
+}
+
+// Wide stem steps (huge dense operand x small DENSE operand, 128 columns per pass) on the CTA-pair kernel with the
+// stem kernel's sorted-pattern epilogue: one launch covers all passes.  e: big operand as A (dense [K][M], M % 128 == 0),
+// small operand as e.B with leading dimension ldb (dense [K][N], N % 128 == 0).  Returns -1 when the operands do not meet
+// the alignment rules of the bulk copies (caller falls back to the 1-CTA stem kernel).
+int tnb_launch_c64_pair_staged(tnb_ctx* ctx, const StemArgs& e, int64_t Nsmall, int64_t ldb, bool rel_small) {
+    if (!ctx->gemm_pair || !e.additive || (e.M % TC_BM) != 0 || (Nsmall % PR_NT) != 0 || e.M <= TC_BM) return -1;
+    TcArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = (const float2*)e.A; a.B = (const float2*)e.B; a.C = (float2*)e.C;
+    a.M = (uint32_t)e.M; a.N = (uint32_t)Nsmall; a.K = (uint32_t)e.K;
+    a.lda = e.lda; a.ldb = ldb;
+    a.conjA = e.conjA; a.conjB = e.conjB;
+    a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
+    a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
+    a.splitk = 1;
+    a.kb_per_split = (uint32_t)((e.K + TC_BK - 1) / TC_BK);
+    a.st_hi = e.hi; a.st_rel = e.rel; a.st_pos = e.pos;
+    a.st_run_shift = 0;
+    while ((1 << (a.st_run_shift + 1)) <= e.run) a.st_run_shift++;
+    a.st_vec2 = (e.run >= 2 && e.even && ((uintptr_t)e.C % 16) == 0) ? 1 : 0;
+    a.st_rel_small = rel_small ? 1 : 0;
+    if (!tc_acc_ok(a)) return -1;
+    return launch_tc_pair<true>(ctx, a);
 }

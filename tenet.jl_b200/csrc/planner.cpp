@@ -312,6 +312,8 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         for (int64_t j = 0; j < cnt * passes && even; j += R) if (S.st_rel[(size_t)j] & 1) even = false;
         if (wide && !additive) continue;       // the 128-column form has no room for the general rank table
         S.st_additive = additive; S.st_even = even;
+        S.st_rel_small = true;
+        for (int64_t v : S.st_rel) if (v < 0 || v >= ((int64_t)1 << 31)) { S.st_rel_small = false; break; }
         if (getenv("TNB_DEBUG_STEM"))
             fprintf(stderr, "[stem] M=%lld N=%lld K=%lld big=%lld small=%lld tc=%d swap=%d TM=%lld ncol=%lld passes=%lld run=%lld additive=%d even=%d contig=%d\n",
                     (long long)S.M, (long long)S.N, (long long)S.K, (long long)Mb, (long long)Ns, (int)!simt, sw, (long long)TM,

@@ -75,6 +75,7 @@ struct StepSpec {
     bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
     int32_t st_npass = 1, st_ncol = 0;   // passes over the small operand's columns, columns per pass
     bool st_additive = false, st_even = false;   // see StemArgs
+    bool st_rel_small = false;                   // every entry of st_rel fits an int32 (run bases kept in shared memory)
     int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
@@ -109,7 +110,9 @@ struct tnb_ctx {
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
     int rank = 0, nranks = 1;
+    void* multi = nullptr;   // tnb_multi: worker contexts + communicator of tnb_multi_contract_path (multi.cu)
 };
+void tnb_multi_release(tnb_ctx* ctx);
 
 int tnb_set_error(tnb_ctx* ctx, int code, const char* fmt, ...);
 #define TNB_CUDA_CHECK(ctx, expr)                                                              \
@@ -170,6 +173,7 @@ struct StemArgs {
 int tnb_launch_stem(tnb_ctx* ctx, int dtype, const StemArgs& a);
 bool tnb_stem_tc_shape_ok(int64_t Mbig, int64_t Nsmall, int64_t K);
 int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass);
+int tnb_launch_c64_pair_staged(tnb_ctx* ctx, const StemArgs& e, int64_t Nsmall, int64_t ldb, bool rel_small);   // -1: not eligible
 int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass);
 
 // kernels_c128_dmma.cu

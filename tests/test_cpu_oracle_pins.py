@@ -129,3 +129,16 @@ def test_package_generators_match_oracle_generators():
     a, i = onet.expectation_network(ref, *onet.ising_1d_mpo(n, 0.7, 1.3))
     v2, _ = orc.contract_path(a, i, onet.sweep_steps(n))
     assert abs(v - v2) < 1e-12 and abs(v.imag) < 1e-12
+
+
+def test_integer_valued_mps_oracle_exact():
+    """test/unit/mps.jl:63-69,89 input through the oracle's contract_path: exact integers (< 2^53) in float64."""
+    from oracle import einsum_oracle as orc
+    a2 = np.arange(1, 17, dtype=np.int64).reshape(4, 4, order="F")
+    a3 = np.arange(1, 65, dtype=np.int64).reshape(4, 4, 4, order="F")
+    arrays = [a2, a3, a3, a3, a2]
+    inds = [("b12", "p1"), ("b12", "b23", "p2"), ("b23", "b34", "p3"), ("b34", "b45", "p4"), ("b45", "p5")]
+    out = ("p1", "p2", "p3", "p4", "p5")
+    got, gi = orc.contract_path([a.astype(np.float64) for a in arrays], inds, [(0, 1), (5, 2), (6, 3), (7, 4)], out)
+    ref = np.einsum("ap,abq,bcr,cds,dt->pqrst", *arrays)
+    assert tuple(gi) == out and np.array_equal(got, ref.astype(np.float64))

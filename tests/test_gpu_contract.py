@@ -6,6 +6,8 @@ import pytest
 from oracle import einsum_oracle as orc
 from oracle import statevector as sv
 
+from tolerances import C128_BOUND, C64_PATH_BOUND, C64_STEP_BOUND  # noqa: F401
+
 pytestmark = pytest.mark.gpu
 
 
@@ -18,7 +20,7 @@ def _rel(got, ref):
     return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
 
 
-@pytest.mark.parametrize("dt,tol", [(np.complex128, 1e-12), (np.complex64, 5e-5), (np.float64, 1e-12)])
+@pytest.mark.parametrize("dt,tol", [(np.complex128, C128_BOUND), (np.complex64, C64_PATH_BOUND), (np.float64, C128_BOUND)])
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_random_regular_closed(ctx, dt, tol, seed):
     import tenet_jl_b200 as tb
@@ -60,7 +62,7 @@ def test_hyperindex_batch(ctx):
     assert _rel(got, ref) < 1e-12
 
 
-@pytest.mark.parametrize("dt,tol", [(np.complex128, 1e-12), (np.complex64, 5e-5)])
+@pytest.mark.parametrize("dt,tol", [(np.complex128, C128_BOUND), (np.complex64, C64_PATH_BOUND)])
 def test_sliced_equals_unsliced_and_oracle(ctx, dt, tol):
     import tenet_jl_b200 as tb
     tn = tb.workloads.random_regular_network(n=24, bond=3, dtype=dt, seed=5)
@@ -136,7 +138,7 @@ def test_gauge_trick_K4(ctx):
     assert abs(v / nrm - (-1.3 * (n - 1))) < 1e-9
 
 
-@pytest.mark.parametrize("dt,tol", [(np.complex64, 2e-4), (np.complex128, 1e-11)])
+@pytest.mark.parametrize("dt,tol", [(np.complex64, C64_PATH_BOUND), (np.complex128, 10 * C128_BOUND)])
 def test_circuit_amplitude_vs_statevector(ctx, dt, tol):
     import tenet_jl_b200 as tb
     tn, (nq, gates, bits) = tb.workloads.sycamore_amplitude_network(rows=4, cols=3, cycles=8, seed=11, removed=((0, 1),), dtype=dt)
@@ -196,3 +198,82 @@ def test_error_paths(ctx):
         tb.contract(tn, path=tb.ContractionPath([(0, 2)]))                      # id does not exist
     with pytest.raises(ValueError):
         tb.contract(tb.TensorNetwork([]))
+
+
+def _integer_mps_arrays():
+    """test/unit/mps.jl:63-69: MPS([reshape(1:16,4,4), reshape(1:64,4,4,4) x 3, reshape(1:16,4,4)]) (Julia is
+    column-major: order="F"), default order (:l, :r, :o)."""
+    a2 = np.arange(1, 17, dtype=np.int64).reshape(4, 4, order="F")
+    a3 = np.arange(1, 65, dtype=np.int64).reshape(4, 4, 4, order="F")
+    return [a2, a3, a3, a3, a2]
+
+
+def test_integer_valued_mps_contract_is_exact(ctx):
+    """Reference-held input (test/unit/mps.jl:63-69,89): the 5-site integer-valued MPS the reference contracts in its
+    canonize tests.  Int64 promotes to Float64 on the host (a1 (v)); every product and partial sum is an integer below
+    2^53, so the 4^5-element result must equal the exact integer contraction BIT FOR BIT, whatever the summation order."""
+    import tenet_jl_b200 as tb
+    arrays = _integer_mps_arrays()
+    psi = tb.MPS(arrays)
+    got = tb.contract(psi)
+    assert got.parent.dtype == np.float64 and got.parent.size == 4 ** 5
+    # exact integer reference: sites are (r, o), (l, r, o) x 3, (l, o)
+    ref = np.einsum("ap,abq,bcr,cds,dt->pqrst", arrays[0], arrays[1], arrays[2], arrays[3], arrays[4])
+    assert ref.max() < 2 ** 53
+    plugs = [tb.components.plug(i) for i in range(1, 6)]
+    g = np.transpose(got.parent, [got.inds.index(i) for i in plugs])
+    assert np.array_equal(g, ref.astype(np.float64))
+
+
+def test_allreduce_refuses_partial_sum_without_communicator(ctx, monkeypatch):
+    """with WORLD_SIZE > 1 in the environment but no communicator on the context, contract_distributed must
+    raise instead of returning this rank's partial slice sum."""
+    import tenet_jl_b200 as tb
+    tn, _ = tb.workloads.sycamore_amplitude_network(rows=3, cols=3, cycles=6, seed=3, removed=(), dtype=np.complex64)
+    path = tb.einexpr(tn, ntrials=4, seed=0, max_log2_size=4)
+    plan = tb.ContractionPlan(tn, path, ctx=ctx)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    assert ctx.lib.tnb_comm_size(ctx.handle) == 1
+    with pytest.raises(tb.TnbError):
+        tb.distributed.contract_distributed(plan, ctx)
+    plan.close()
+
+
+def test_empty_slice_range_zeroes_the_output(ctx):
+    """accumulate = 0 with an empty slice range (a rank that owns no slice) must leave zeros, not stale data."""
+    import tenet_jl_b200 as tb
+    tn, _ = tb.workloads.sycamore_amplitude_network(rows=3, cols=3, cycles=6, seed=3, removed=(), dtype=np.complex64)
+    path = tb.einexpr(tn, ntrials=4, seed=0, max_log2_size=4)
+    plan = tb.ContractionPlan(tn, path, ctx=ctx)
+    plan.execute(0, 1, plan.nslices, accumulate=False)
+    assert abs(plan.result().item()) > 0
+    plan.execute(plan.nslices, 1, plan.nslices, accumulate=False)      # empty range
+    assert plan.result().item() == 0
+    plan.close()
+
+
+def test_simt_mode_k_reduction_is_exact_fp32(ctx):
+    """TNB_C64_SIMT must keep tensor-core rounding out of the k-reduction steps too: in SIMT mode a
+    16 x 32 x K step agrees bitwise with ... itself under TNB_KRED_MMA-independent FMA arithmetic, and differs from the
+    default (mma.sync 3xTF32) result only within the step bound."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(8)
+    K = 1 << 15
+    a = (rng.standard_normal((16, K)) + 1j * rng.standard_normal((16, K))).astype(np.complex64)
+    b = (rng.standard_normal((32, K)) + 1j * rng.standard_normal((32, K))).astype(np.complex64)
+    ta, tb_ = tb.Tensor(a, ("m", "k")), tb.Tensor(b, ("n", "k"))
+    c_tc = tb.binary_einsum(ta, tb_).parent.copy()
+    assert ctx.last_kernel == "stream"
+    ctx.set_option(tb._lib.TNB_OPT_C64_MODE, tb._lib.TNB_C64_SIMT)
+    try:
+        c1 = tb.binary_einsum(ta, tb_).parent.copy()
+        assert ctx.last_kernel == "stream"
+        c2 = tb.binary_einsum(ta, tb_).parent.copy()
+    finally:
+        ctx.set_option(tb._lib.TNB_OPT_C64_MODE, tb._lib.TNB_C64_TF32X3)
+    ref = a.astype(np.complex128) @ b.astype(np.complex128).T
+    assert np.array_equal(c1, c2)
+    assert np.abs(c1 - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
+    assert np.abs(c_tc - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
+    assert not np.array_equal(c1, c_tc), "SIMT mode still runs the tensor-core k-reduction"

@@ -5,6 +5,8 @@
 import numpy as np
 import pytest
 
+from tolerances import C128_BOUND, C64_STEP_BOUND
+
 pytestmark = pytest.mark.gpu
 
 
@@ -25,7 +27,7 @@ def test_tc_matches_oracle(ctx, M, N, K):
     ref = a.astype(np.complex128) @ b.astype(np.complex128).T
     got = c.parent
     err = np.abs(got - ref).max() / np.abs(ref).max()
-    assert err < 2e-5, f"rel err {err:.2e}"
+    assert err < C64_STEP_BOUND, f"rel err {err:.2e}"
     # same step on the exact-FP32 generic kernel: both must sit within FP32 noise of the c128 truth
     ctx.set_option(tb._lib.TNB_OPT_FORCE_KERNEL, 1)
     try:
@@ -34,7 +36,7 @@ def test_tc_matches_oracle(ctx, M, N, K):
     finally:
         ctx.set_option(tb._lib.TNB_OPT_FORCE_KERNEL, 0)
     err2 = np.abs(c2.parent - ref).max() / np.abs(ref).max()
-    assert err2 < 2e-5
+    assert err2 < C64_STEP_BOUND
     assert err < 20 * max(err2, 1e-7), f"3xTF32 error {err:.2e} vs FP32-SIMT error {err2:.2e}"
 
 
@@ -57,7 +59,7 @@ def test_pair_kernel_bit_identical_to_single_cta(ctx, M, N, K):
         finally:
             ctx.set_option(tb._lib.TNB_OPT_GEMM_PAIR, 1)
     ref = np.conj(a).astype(np.complex128) @ b.astype(np.complex128).T
-    assert np.abs(out[1] - ref).max() / np.abs(ref).max() < 2e-5
+    assert np.abs(out[1] - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
     assert np.array_equal(out[0], out[1]), f"max diff {np.abs(out[0] - out[1]).max():.3e}"
 
 
@@ -75,11 +77,11 @@ def test_tc_conj_swap_and_scatter(ctx):
         c = tb.binary_einsum(ta, tb_, out=out)
         assert ctx.last_kernel == "c64_tf32x3"
         r = ref if out is None else np.einsum("abcdef->eadcbf", ref)
-        assert np.abs(c.parent - r).max() / np.abs(r).max() < 2e-5
+        assert np.abs(c.parent - r).max() / np.abs(r).max() < C64_STEP_BOUND
     a2, b2 = crand(rng, (64, 32)), crand(rng, (256, 32))     # M = 64 -> swapped roles
     c = tb.binary_einsum(tb.Tensor(a2, ("m", "k")).conj(), tb.Tensor(b2, ("n", "k")))
     ref = np.conj(a2).astype(np.complex128) @ b2.astype(np.complex128).T
-    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 2e-5
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
 
 
 def test_simt_mode_option(ctx):
@@ -94,7 +96,7 @@ def test_simt_mode_option(ctx):
         ctx.set_option(tb._lib.TNB_OPT_C64_MODE, tb._lib.TNB_C64_TF32X3)
 
 
-@pytest.mark.parametrize("dt,tol", [(np.complex64, 1e-5), (np.complex128, 1e-13), (np.float64, 1e-13)])
+@pytest.mark.parametrize("dt,tol", [(np.complex64, C64_STEP_BOUND), (np.complex128, C128_BOUND), (np.float64, C128_BOUND)])
 @pytest.mark.parametrize("M,N", [(1, 1), (2, 3), (4, 4), (1, 4)])
 def test_thin_reduction(ctx, dt, tol, M, N):
     """amplitude-closing dot products: M*N <= 16, K = 2^20 (+ a ragged K)."""
@@ -111,7 +113,7 @@ def test_thin_reduction(ctx, dt, tol, M, N):
         assert np.abs(c.parent - ref).max() / np.abs(ref).max() < tol * 10
 
 
-@pytest.mark.parametrize("dt,tol", [(np.complex64, 1e-5), (np.complex128, 1e-13)])
+@pytest.mark.parametrize("dt,tol", [(np.complex64, C64_STEP_BOUND), (np.complex128, C128_BOUND)])
 @pytest.mark.parametrize("M,N", [(8, 32), (2, 4), (16, 32), (4, 128), (6, 12), (32, 16), (16, 16), (16, 8)])
 def test_k_reduction_kernel(ctx, dt, tol, M, N):
     """small M x N, huge K, dense operands with the free index fastest (the environment-closing steps of a sliced
@@ -180,7 +182,7 @@ def test_tc_misaligned_view_falls_back(ctx):
     v = t.view(("m", slice(1, 129)))
     c = tb.binary_einsum(v, tb.Tensor(b, ("n", "k")))
     ref = big[1:129].astype(np.complex128) @ b.astype(np.complex128).T
-    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < 2e-5
+    assert np.abs(c.parent - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
 
 
 @pytest.mark.parametrize("dt,tol", [(np.complex64, 2e-6), (np.complex128, 1e-13)])
@@ -240,11 +242,43 @@ def test_stem_tc_kernel(ctx, N, K):
         assert ctx.last_kernel == "stem_tc", ctx.last_kernel
         r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
         err = np.abs(c.parent - r).max() / np.abs(r).max()
-        assert err < 1e-5, err
+        assert err < C64_STEP_BOUND, err
     c = tb.binary_einsum(tb_.conj(), ta)
     assert ctx.last_kernel == "stem_tc"
     r = np.transpose(np.tensordot(a.astype(hi), np.conj(b).astype(hi), axes=([17], [1])), [17] + list(range(17)))
-    assert np.abs(c.parent - r).max() / np.abs(r).max() < 1e-5
+    assert np.abs(c.parent - r).max() / np.abs(r).max() < C64_STEP_BOUND
+
+
+@pytest.mark.parametrize("N,K", [(128, 128), (256, 64), (512, 128), (128, 72)])
+def test_wide_stem_on_cta_pairs_bit_identical(ctx, N, K):
+    """128-column stem passes with a dense small operand run on the CTA-pair kernel (staged sorted-pattern epilogue);
+    with TNB_OPT_GEMM_PAIR = 0 the 1-CTA stem kernel takes them.  Same MMA order per output element: bit-identical,
+    for every consumer layout (coalesced write-out through the planner's sorted tile pattern), both orientations,
+    conj, beta = 1."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(N * 17 + K)
+    a = crand(rng, (2,) * 17 + (K,))
+    b = crand(rng, (N, K))
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]).conj(), tb.Tensor(b, ["n", "k"])
+    ref = np.tensordot(np.conj(a).astype(np.complex128), b.astype(np.complex128), axes=([17], [1]))
+    l0 = ctx.launch_count
+    for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8], big[8:] + ["n"] + big[:8]]:
+        res = {}
+        for pair in (0, 1):
+            ctx.set_option(tb._lib.TNB_OPT_GEMM_PAIR, pair)
+            try:
+                res[pair] = tb.binary_einsum(ta, tb_, out=out).parent.copy()
+                assert ctx.last_kernel == "stem_tc", ctx.last_kernel
+            finally:
+                ctx.set_option(tb._lib.TNB_OPT_GEMM_PAIR, 1)
+        r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        assert np.abs(res[1] - r).max() / np.abs(r).max() < C64_STEP_BOUND
+        assert np.array_equal(res[0], res[1]), f"out={out}: max diff {np.abs(res[0] - res[1]).max():.3e}"
+    c0 = tb.binary_einsum(tb_, ta)                     # swapped orientation
+    assert ctx.last_kernel == "stem_tc"
+    r = np.transpose(ref, [17] + list(range(17)))
+    assert np.abs(c0.parent - r).max() / np.abs(r).max() < C64_STEP_BOUND
 
 
 def test_stem_tc_rank_table_path(ctx, monkeypatch):
@@ -263,7 +297,7 @@ def test_stem_tc_rank_table_path(ctx, monkeypatch):
         assert ctx.last_kernel == "stem_tc", ctx.last_kernel
         r = np.transpose(ref, [(big + ["n"]).index(i) for i in out])
         err = np.abs(c.parent - r).max() / np.abs(r).max()
-        assert err < 1e-5, err
+        assert err < C64_STEP_BOUND, err
 
 
 @pytest.mark.parametrize("N,K", [(128, 256), (256, 512), (128, 200)])
@@ -286,4 +320,4 @@ def test_stem_tc_long_k(ctx, N, K):
         assert ctx.last_kernel == ("stem_tc" if K <= kmax and K % 8 == 0 else "c64_tf32x3"), ctx.last_kernel
         r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
         err = np.abs(c.parent - r).max() / np.abs(r).max()
-        assert err < 1e-5, err
+        assert err < C64_STEP_BOUND, err
