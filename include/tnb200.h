@@ -46,6 +46,7 @@ extern "C" {
 /* precision policy for ComplexF32 / Float32 tensor-core GEMM steps (tnb_ctx_set_option) */
 #define TNB_OPT_C64_MODE     1   /* value: TNB_C64_SIMT | TNB_C64_TF32X3 | TNB_C64_TF32X3_FAST */
 #define TNB_OPT_FORCE_KERNEL 2   /* value: 0 auto, 1 generic table kernel only (debug/parity) */
+#define TNB_OPT_CUDA_GRAPH   4   /* value: 1 (default) un-sliced plans are captured once and replayed as ONE CUDA graph, 0 direct launches */
 #define TNB_OPT_GEMM_PAIR    3   /* value: 1 (default) c64 GEMM steps on CTA pairs (cta_group::2), 0 the 1-CTA kernel */
 #define TNB_C64_SIMT   0         /* exact FP32 FMA (BLAS-equivalent rounding)                  */
 #define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo split; TMEM chunks of 64 k drained into RN fp32 totals (default) */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libtnb200.so")
 
 TNB_OK, TNB_EINVAL, TNB_ENOMEM, TNB_ECUDA, TNB_ENCCL, TNB_EUNSUPPORTED = range(6)
 TNB_C128, TNB_C64, TNB_F64, TNB_F32 = range(4)
-TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL, TNB_OPT_GEMM_PAIR = 1, 2, 3
+TNB_OPT_C64_MODE, TNB_OPT_FORCE_KERNEL, TNB_OPT_GEMM_PAIR, TNB_OPT_CUDA_GRAPH = 1, 2, 3, 4
 TNB_C64_SIMT, TNB_C64_TF32X3, TNB_C64_TF32X3_FAST = 0, 1, 2
 KERNEL_NAMES = {0: "generic", 1: "c64_tf32x3", 2: "c128_dmma", 3: "stream", 4: "splitk", 5: "stem", 6: "stem_tc"}
 

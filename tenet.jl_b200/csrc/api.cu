@@ -389,6 +389,7 @@ int tnb_plan_create_dry(const tnb_tensor* leaves, int32_t nleaves, const int32_t
 int tnb_plan_destroy(tnb_ctx* ctx, tnb_plan* plan) {
     if (!plan) return TNB_OK;
     for (auto& e : plan->ev) cudaEventDestroy(e);
+    for (auto& g : plan->gexec) if (g) cudaGraphExecDestroy(g);
     if (!plan->dry && ctx) {
         tnb_free(ctx, plan->arena);
         tnb_free(ctx, plan->tables);
@@ -530,6 +531,38 @@ int tnb_plan_execute(tnb_ctx* ctx, tnb_plan* P, int64_t slice_begin, int64_t sli
     if (root_hoisted) {
         // no slice dependence at all: one pass (a rank with an empty slice range contributes nothing)
         if (slice_begin != 0) return acc ? TNB_OK : zero_out();
+        // Small un-sliced networks (configs[0]: 63 launches of a few microseconds each) are launch-overhead bound
+        // (docs/src/manual/reactant.md:52-56 makes the same observation for the reference): the step sequence has the
+        // same pointers on every execute, so it is captured once per accumulate flag and replayed as ONE graph launch.
+        const int gi = acc ? 1 : 0;
+        if (ctx->use_graphs && !P->profiling && !P->graph_failed) {
+            if (!P->gexec[gi]) {
+                cudaGraph_t graph = nullptr;
+                const int64_t l0 = ctx->launches;
+                bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                int crc = TNB_OK;
+                if (ok) {
+                    for (int s : P->order_hoisted)
+                        if ((crc = run(s, acc))) break;
+                    ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr && crc == TNB_OK;
+                }
+                if (ok) ok = cudaGraphInstantiate(&P->gexec[gi], graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                P->glaunches[gi] = ctx->launches - l0;
+                ctx->launches = l0;
+                if (!ok) {                      // not capturable on this driver / a launch failed: direct launches from now on
+                    cudaGetLastError();
+                    P->gexec[gi] = nullptr;
+                    P->graph_failed = true;
+                    if (crc) return crc;
+                }
+            }
+            if (P->gexec[gi]) {
+                TNB_CUDA_CHECK(ctx, cudaGraphLaunch(P->gexec[gi], ctx->stream));
+                ctx->launches += P->glaunches[gi];
+                return TNB_OK;
+            }
+        }
         for (int s : P->order_hoisted)
             if ((rc = run(s, acc))) return rc;
         collect();

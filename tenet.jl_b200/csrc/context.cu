@@ -81,6 +81,9 @@ int tnb_ctx_set_option(tnb_ctx* ctx, int option, int64_t value) {
         case TNB_OPT_FORCE_KERNEL:
             ctx->force_generic = value ? 1 : 0;
             return TNB_OK;
+        case TNB_OPT_CUDA_GRAPH:
+            ctx->use_graphs = value ? 1 : 0;
+            return TNB_OK;
         case TNB_OPT_GEMM_PAIR:
             ctx->gemm_pair = value ? 1 : 0;
             return TNB_OK;

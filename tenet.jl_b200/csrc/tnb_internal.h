@@ -104,6 +104,7 @@ struct tnb_ctx {
     int sm_count = 148;
     int c64_mode = TNB_C64_TF32X3;
     int force_generic = 0;
+    int use_graphs = 1;      // replay un-sliced plans as one CUDA graph (TNB_OPT_CUDA_GRAPH)
     int gemm_pair = 1;       // c64 GEMM steps on CTA pairs (TNB_OPT_GEMM_PAIR; env TNB_GEMM_PAIR=0 sets the default off)
     int last_kernel = -1;    // kernel id chosen by the most recent tnb_binary_einsum (introspection)
     // comm
@@ -230,6 +231,11 @@ struct tnb_plan {
     std::vector<cudaEvent_t> ev;          // 2 per step
     std::vector<double> step_ms;          // accumulated
     std::vector<int64_t> step_runs;
+    // CUDA graph of an UN-SLICED path (every step is slice-invariant: same pointers on every execute), one per
+    // accumulate flag; captured on the first execute, replayed afterwards (tnb_plan_execute)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int64_t glaunches[2] = {0, 0};
+    bool graph_failed = false;
 };
 
 int tnb_plan_build(const tnb_tensor* leaves, int32_t nleaves, const int32_t* steps, int32_t nsteps,

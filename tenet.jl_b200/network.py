@@ -252,3 +252,44 @@ def contract(tn, path: Optional[ContractionPath] = None, optimizer: str = "greed
     finally:
         plan.close()
     return res
+
+
+def multi_contract(tn, path: ContractionPath, ngpus: int, output: Optional[Sequence[Hashable]] = None,
+                   ctx: Optional[Context] = None) -> Tensor:
+    """`contract(tn; path)` over `ngpus` GPUs of this box from ONE process (tnb_multi_contract_path): the leaves live on
+    `ctx`'s device, the library broadcasts them, deals slice s to GPU s mod ngpus (one host thread + one context per
+    device), sums the per-GPU accumulators with a single NCCL all-reduce and returns the result on `ctx`'s device.
+    This is what a single Julia task calling `contract` binds; the one-process-per-GPU form is
+    `distributed.contract_distributed`."""
+    if not isinstance(tn, TensorNetwork):
+        tn = TensorNetwork(getattr(tn, "tensors"))
+    ctx = ctx or default_context()
+    lib = _lib.load_library()
+    sliced = tuple(path.sliced)
+    if output is None:
+        output = path.output if path.output else tuple(i for i in tn.inds("open") if i not in sliced)
+    output = tuple(output)
+    dt = _promote_dtype(*[t.dtype for t in tn.tensors])
+    code = _lib.DTYPE_CODE[dt]
+    modes = {}
+    for t in tn.tensors:
+        for i in t.inds:
+            modes.setdefault(i, len(modes))
+    sizes = tn.sizes()
+    n = len(tn.tensors)
+    keep_alive = []
+    descs = (tnb_tensor * n)()
+    for k, t in enumerate(tn.tensors):
+        arr = t.device(ctx, dt)
+        d, keep = make_desc(arr.buffer.handle, arr.offset, code, arr.shape, arr.strides, [modes[i] for i in t.inds], t._conj)
+        descs[k] = d
+        keep_alive += [arr, keep]
+    oshape = [sizes[i] for i in output]
+    out_array = B200Array.zeros(oshape, dt, ctx)
+    dout, keep = make_desc(out_array.buffer.handle, 0, code, oshape, out_array.strides, [modes[i] for i in output])
+    keep_alive.append(keep)
+    steps = (C.c_int32 * max(2 * len(path.steps), 1))(*[x for s in path.steps for x in s])
+    sm = (C.c_int32 * max(len(sliced), 1))(*[modes[i] for i in sliced])
+    check(ctx.handle, lib.tnb_multi_contract_path(ctx.handle, descs, n, steps, len(path.steps), sm, len(sliced),
+                                                  C.byref(dout), int(ngpus)))
+    return Tensor(out_array, output)

@@ -277,3 +277,30 @@ def test_simt_mode_k_reduction_is_exact_fp32(ctx):
     assert np.abs(c1 - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
     assert np.abs(c_tc - ref).max() / np.abs(ref).max() < C64_STEP_BOUND
     assert not np.array_equal(c1, c_tc), "SIMT mode still runs the tensor-core k-reduction"
+
+
+def test_unsliced_plan_replays_as_cuda_graph(ctx):
+    """Un-sliced plans are captured once and replayed as one CUDA graph (TNB_OPT_CUDA_GRAPH, default on): same result
+    bit for bit as direct launches, on the first (capturing) execute and on replays; launch accounting unchanged."""
+    import tenet_jl_b200 as tb
+    tn, psi = tb.workloads.mps_norm_network(12, 32, np.complex128, seed=1)
+    path = tb.workloads.zipper_path(12)
+    vals, launches = {}, {}
+    for graphs in (0, 1):
+        ctx.set_option(tb._lib.TNB_OPT_CUDA_GRAPH, graphs)
+        try:
+            plan = tb.ContractionPlan(tn, path, ctx=ctx)
+            out = []
+            l0 = ctx.launch_count
+            for _ in range(3):
+                plan.zero_output()
+                plan.execute(0, 1, plan.nslices, accumulate=True)
+                out.append(plan.result().item())
+            launches[graphs] = ctx.launch_count - l0
+            vals[graphs] = out
+            plan.close()
+        finally:
+            ctx.set_option(tb._lib.TNB_OPT_CUDA_GRAPH, 1)
+    assert vals[0][0] == vals[0][1] == vals[0][2] == vals[1][0] == vals[1][1] == vals[1][2]
+    assert abs(vals[1][0] - 1.0) < C128_BOUND
+    assert launches[0] == launches[1] > 0
