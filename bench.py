@@ -181,8 +181,16 @@ def cpu_sample(tb, tn, path, budget_macs_log2=38.5, deadline_s=40.0):
     arrays = [t.parent for t in tn.tensors]
     cplx = np.iscomplexobj(arrays[0])
     unit = 8.0 if cplx else 2.0
-    if len(path.sliced) == 0 and path.log2_macs > budget_macs_log2 + 1.0:
-        return cpu_sample_prefix(orc, arrays, inputs, path, unit, deadline_s)
+    if len(path.sliced) == 0:
+        # hand-written paths (zipper, env sweep, PEPS boundary) carry no cost estimate: count the MACs here
+        macs, _, _ = orc.path_flops(inputs, tn.sizes(), path.steps)
+        log2_macs = float(np.log2(max(float(macs), 1.0)))
+        if log2_macs > budget_macs_log2 + 0.5:
+            return cpu_sample_prefix(orc, arrays, inputs, path, unit, deadline_s, log2_macs)
+        t0 = time.perf_counter()
+        orc.contract_path(arrays, inputs, path.steps)
+        dt = time.perf_counter() - t0
+        return unit * float(macs), dt, f"the whole path (2^{log2_macs:.1f} MACs); numpy/OpenBLAS permute->reshape->gemm restatement"
     p = subslice_path(tb, tn, path, budget_macs_log2)
     sl = list(p.sliced)
     t0 = time.perf_counter()
@@ -195,7 +203,7 @@ def cpu_sample(tb, tn, path, budget_macs_log2=38.5, deadline_s=40.0):
     return flops, dt, what + "; numpy/OpenBLAS permute->reshape->gemm restatement"
 
 
-def cpu_sample_prefix(orc, arrays, inds, path, unit, deadline_s):
+def cpu_sample_prefix(orc, arrays, inds, path, unit, deadline_s, log2_macs_total):
     """oracle.contract_path step by step with a wall-clock deadline (un-sliced, long paths: configs[4])."""
     n = len(arrays)
     total = {}
@@ -226,7 +234,7 @@ def cpu_sample_prefix(orc, arrays, inds, path, unit, deadline_s):
             break
     dt = time.perf_counter() - t0
     return unit * macs, dt, (f"the first {done} of {len(path.steps)} pairwise steps of the same path (2^{np.log2(max(macs, 1)):.1f} of "
-                             f"2^{path.log2_macs:.1f} MACs, stopped at the first step boundary after {deadline_s:.0f} s); "
+                             f"2^{log2_macs_total:.1f} MACs, stopped at the first step boundary after {deadline_s:.0f} s); "
                              f"numpy/OpenBLAS permute->reshape->gemm restatement")
 
 

@@ -241,19 +241,36 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) einsum_c128_dmma_kernel(const E
 
 }  // namespace
 
-// split-K factor for this tile shape (same policy as the generic kernel)
+// split-K factor for this tile shape.  Two reasons to split: (1) fewer tiles than SMs (same policy as the generic
+// kernel); (2) WAVE QUANTISATION — one CTA per SM, so `tiles` CTAs run in ceil(tiles / SMs) waves and the last one may be
+// nearly empty (configs[4]'s bulk GEMM: 768 tiles on 148 SMs = 5.19 waves -> 6, 13.5 % of the machine idle).  Splitting K
+// by s in {2, 3, 4} multiplies the CTA count; the s with the best wave efficiency is taken when it beats the unsplit grid
+// by more than the cost of the partial-sum pass (s x M x N elements written + read by the deterministic reducer).
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
                            int64_t* ws_elems) {
     *kchunk = K;
     *ws_elems = 0;
     int64_t tiles = ((M + ZT_M - 1) / ZT_M) * ((N + ZT_N - 1) / ZT_N) * L;
     const int64_t sms = ctx ? ctx->sm_count : 148;
-    if (tiles >= sms || K < 128) return 1;
-    int64_t want = (2 * sms + tiles - 1) / tiles;
-    int64_t maxs = K / 32;
-    int64_t s = want < maxs ? want : maxs;
     const int64_t WS_MAX = (int64_t)1 << 24;
-    while (s > 1 && s * M * N * L > WS_MAX) s--;
+    int64_t s = 1;
+    if (tiles < sms && K >= 128) {
+        int64_t want = (2 * sms + tiles - 1) / tiles;
+        int64_t maxs = K / 32;
+        s = want < maxs ? want : maxs;
+        while (s > 1 && s * M * N * L > WS_MAX) s--;
+    } else if (tiles >= sms && tiles < 16 * sms && K >= 256) {
+        auto eff = [&](int64_t c) { return (double)c / (double)(((c + sms - 1) / sms) * sms); };
+        // time model per CTA-wave: K/s k-steps of the tile + the partial-sum traffic (s > 1): 3 x 16 B per element of C per split
+        // against ~8 K flops per element at the kernel's rate; expressed as a fraction of the unsplit runtime
+        double best = eff(tiles);
+        for (int64_t c = 2; c <= 4; c++) {
+            if (K / c < 128 || c * M * N * L > 4 * WS_MAX) continue;
+            const double penalty = 1.0 + (double)c * 48.0 / (8.0 * (double)K / 24e12 * 5e12);   // bytes at ~5 TB/s vs flops at ~24 TFLOP/s
+            const double e = eff(tiles * c) / penalty;
+            if (e > best * 1.03) { best = e; s = c; }
+        }
+    }
     if (s <= 1) return 1;
     int64_t kc = (K + s - 1) / s;
     kc = (kc + ZT_K - 1) / ZT_K * ZT_K;

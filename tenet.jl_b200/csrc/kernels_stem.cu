@@ -49,8 +49,12 @@ __device__ __forceinline__ float2 czero(float2*) { return make_float2(0.f, 0.f);
 __device__ __forceinline__ double2 czero(double2*) { return make_double2(0., 0.); }
 
 // E = float2 (VM = 2: one 16-byte load covers two m) or double2 (VM = 1)
+// Occupancy: the kernel is a latency machine (load phase, rank-ordered staging, write-out phase per tile), so the bytes in
+// flight per SM are (resident CTAs) x 256 threads x (loads in flight per thread) x 16 B.  ncu r2 on configs[4]'s
+// 1024^2 x 6 x 6 complex128 step: 104 registers -> 2 CTAs per SM, 21 % of DRAM throughput.  The accumulators need
+// sizeof(E)/4 * VM * NMAX registers; with <= 16 of them the kernel is held to 64 registers (4 CTAs per SM), with <= 32 to 80 (3 CTAs).
 template <typename E, int VM, int NMAX>
-__global__ void __launch_bounds__(ST_THREADS) stem_kernel(const StemArgs p) {
+__global__ void __launch_bounds__(ST_THREADS, (sizeof(E) / 4 * VM * NMAX <= 16) ? 4 : ((sizeof(E) / 4 * VM * NMAX <= 32) ? 3 : 2)) stem_kernel(const StemArgs p) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     const int N = p.N, K = p.K, TM = p.TM;
     E* Bs = reinterpret_cast<E*>(st_smem);                                   // [K][N]
