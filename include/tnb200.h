@@ -46,10 +46,10 @@ extern "C" {
 /* precision policy for ComplexF32 / Float32 tensor-core GEMM steps (tnb_ctx_set_option) */
 #define TNB_OPT_C64_MODE     1   /* value: TNB_C64_SIMT | TNB_C64_TF32X3 | TNB_C64_TF32X3_FAST */
 #define TNB_OPT_FORCE_KERNEL 2   /* value: 0 auto, 1 generic table kernel only (debug/parity) */
+#define TNB_OPT_GEMM_PAIR    3   /* value: 1 (default) c64 GEMM / wide stem steps on CTA pairs (cta_group::2), 0 the 1-CTA kernels */
 #define TNB_OPT_CUDA_GRAPH   4   /* value: 1 (default) un-sliced plans are captured once and replayed as ONE CUDA graph, 0 direct launches */
-#define TNB_OPT_GEMM_PAIR    3   /* value: 1 (default) c64 GEMM steps on CTA pairs (cta_group::2), 0 the 1-CTA kernel */
 #define TNB_C64_SIMT   0         /* exact FP32 FMA (BLAS-equivalent rounding)                  */
-#define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo split; TMEM chunks of 64 k drained into RN fp32 totals (default) */
+#define TNB_C64_TF32X3 1         /* tcgen05 kind::tf32, hi/lo split; TMEM chunks of 128 k drained into RN fp32 totals (default) */
 #define TNB_C64_TF32X3_FAST 2    /* same, whole K chained in TMEM (RZ accumulate bias ~6e-8 * 0.75 K relative) */
 
 #define TNB_MAX_RANK 64
@@ -164,7 +164,7 @@ typedef struct tnb_step_info {
 #define TNB_KERNEL_STREAM    3    /* memory-bound streaming kernel (small K*N)               */
 #define TNB_KERNEL_SPLITK    4    /* split-K reduction (M*N tiny, K huge)                    */
 #define TNB_KERNEL_STEM      5    /* HBM-bound streaming kernel: huge dense operand x tiny operand */
-#define TNB_KERNEL_STEM_TC   6    /* persistent tcgen05 kernel: huge dense operand x small operand (16 <= N <= 64) */
+#define TNB_KERNEL_STEM_TC   6    /* persistent tcgen05 kernels: huge dense operand x small operand (16..128 columns per pass; 128-column passes with a dense small operand run on CTA pairs) */
 int tnb_plan_get_step(const tnb_plan* plan, int32_t step, tnb_step_info* info);
 
 /* per-step device timing (CUDA events on the context stream; one host sync per slice while enabled) */
@@ -188,6 +188,21 @@ int tnb_contract_path(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nleaves,
                       const int32_t* sliced_modes, int32_t nsliced,
                       int64_t slice_begin, int64_t slice_step, int64_t slice_end,
                       const tnb_tensor* out);
+
+/* ---- device-resident thin QR / SVD of a tensor viewed as a matrix -------------------------
+ * Replaces Muscle.tensor_qr_thin(A; inds_q, inds_r, ind_virtual) / tensor_svd_thin(A; inds_u, inds_v, ind_s) behind
+ * canonize! / compress! / evolve! / two-site DMRG (src/Operations/canonize.jl:41,58,97; evolve.jl:62,92;
+ * src/Algorithms/DMRG.jl:338,437), so that the tensors stay on the device between the einsums of the hot path.
+ * Rows of the matrix = row_modes (in that order), columns = the other modes of A in A's order, k = min(m, n):
+ *   A = sum_k Q[row modes.., k] R[k, col modes..]              (Q^H Q = 1, R upper triangular in that matrix view)
+ *   A = sum_k U[row modes.., k] S[k] Vh[k, col modes..]        (S real >= 0, descending, stored in A's dtype)
+ * Q/R/U/S/Vh descriptors give the caller's layouts (any strides / mode order; extents must match; the new mode is
+ * `virtual_mode`).  The factorisation itself is cuSOLVER (geqrf + orgqr / gesvd), dlopen'ed at first use: a missing
+ * libcusolver is TNB_EUNSUPPORTED, never a CPU fallback.  All four dtypes. */
+int tnb_qr_thin(tnb_ctx* ctx, const tnb_tensor* A, const int32_t* row_modes, int32_t nrow, int32_t virtual_mode,
+                const tnb_tensor* Q, const tnb_tensor* R);
+int tnb_svd_thin(tnb_ctx* ctx, const tnb_tensor* A, const int32_t* row_modes, int32_t nrow, int32_t virtual_mode,
+                 const tnb_tensor* U, const tnb_tensor* S, const tnb_tensor* Vh);
 
 /* ---- multi-GPU, single process: tnb_contract_path over `ngpus` devices of this box -------------------------
  * The reference calls `contract` from ONE Julia task, so this is the entry a drop-in `contract(tn; path,

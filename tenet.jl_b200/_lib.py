@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "tnb_ctx_launch_count", "tnb_ctx_last_kernel", "tnb_alloc", "tnb_free", "tnb_upload", "tnb_download", "tnb_memset_zero", "tnb_buf_ptr",
     "tnb_buf_bytes", "tnb_mem_stats", "tnb_mem_trim", "tnb_binary_einsum", "tnb_binary_einsum_result",
     "tnb_plan_create", "tnb_plan_create_dry", "tnb_plan_execute", "tnb_plan_destroy", "tnb_plan_get_info",
-    "tnb_plan_get_step", "tnb_plan_profile", "tnb_plan_get_step_time", "tnb_plan_dump_table", "tnb_plan_dump_step", "tnb_contract_path", "tnb_multi_contract_path", "tnb_comm_unique_id",
+    "tnb_plan_get_step", "tnb_plan_profile", "tnb_plan_get_step_time", "tnb_plan_dump_table", "tnb_plan_dump_step", "tnb_contract_path", "tnb_multi_contract_path", "tnb_qr_thin", "tnb_svd_thin", "tnb_comm_unique_id",
     "tnb_comm_init", "tnb_comm_allreduce_sum", "tnb_comm_size", "tnb_comm_destroy",
 ]
 
@@ -110,6 +110,8 @@ def load_library():
             "tnb_plan_dump_step": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]),
             "tnb_contract_path": (C.c_int, [vp, pt, i32, C.POINTER(i32), i32, C.POINTER(i32), i32, i64, i64, i64, pt]),
             "tnb_multi_contract_path": (C.c_int, [vp, pt, i32, C.POINTER(i32), i32, C.POINTER(i32), i32, pt, i32]),
+            "tnb_qr_thin": (C.c_int, [vp, pt, C.POINTER(i32), i32, i32, pt, pt]),
+            "tnb_svd_thin": (C.c_int, [vp, pt, C.POINTER(i32), i32, i32, pt, pt, pt]),
             "tnb_comm_unique_id": (C.c_int, [vp]),
             "tnb_comm_init": (C.c_int, [vp, vp, i32, i32]),
             "tnb_comm_allreduce_sum": (C.c_int, [vp, vp, sz, i64, i32]),

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["csrc/context.cu", "csrc/api.cu", "csrc/comm.cu", "csrc/multi.cu", "csrc/kernels_generic.cu", "csrc/kernels_c64_tc.cu", "csrc/kernels_c128_dmma.cu", "csrc/kernels_stem.cu", "csrc/planner.cpp"]
+SRC = ["csrc/context.cu", "csrc/api.cu", "csrc/comm.cu", "csrc/multi.cu", "csrc/linalg.cu", "csrc/kernels_generic.cu", "csrc/kernels_c64_tc.cu", "csrc/kernels_c128_dmma.cu", "csrc/kernels_stem.cu", "csrc/planner.cpp"]
 OUT = os.path.join(HERE, "libtnb200.so")
 STAMP = OUT + ".stamp"      # digest of the sources the library was built from (travels with the .so)
 LOCK = OUT + ".lock"

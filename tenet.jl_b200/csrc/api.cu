@@ -120,7 +120,7 @@ int64_t select_kernel(const tnb_ctx* ctx, int dtype, StepSpec& S) {
         S.kernel = TNB_KERNEL_C128_DMMA;
         S.tc_swap = S.N > S.M;
         const int64_t m = S.tc_swap ? S.N : S.M, n = S.tc_swap ? S.M : S.N;
-        S.splitk = tnb_choose_splitk_dmma(ctx, m, n, S.K, S.L, &kchunk, &ws_elems);
+        S.splitk = tnb_choose_splitk_dmma(ctx, m, n, S.K, S.L, &kchunk, &ws_elems, &S.dmma_small);
         S.kchunk = kchunk;
         return ws_elems;
     }
@@ -190,6 +190,7 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         return tnb_launch_einsum_generic(ctx, dtype, g);
     }
     if (S.kernel == TNB_KERNEL_C128_DMMA) {
+        a.pad_ = S.dmma_small;
         if (S.tc_swap) {   // C^T = B * A^T
             std::swap(a.A, a.B); std::swap(a.M, a.N); std::swap(a.conjA, a.conjB);
             std::swap(a.am, a.bn); std::swap(a.ak, a.bk); std::swap(a.al, a.bl); std::swap(a.cm, a.cn);

@@ -10,18 +10,31 @@
 // Complex from real DMMAs:  Cre += Are.Bre + (-Aim).Bim ;  Cim += Are.Bim + Aim.Bre  (4 DMMAs per 8x8x4 complex block).
 // CTA tile 128(m) x 64(n) x 8(k), 256 threads = 8 warps as 4(m) x 2(n), warp tile 32 x 32 complex = 64 accumulator
 // registers per thread.  Operands go global -> shared with cp.async (16 B = one complex, zero-fill at ragged edges) into
-// a 4-stage ring of interleaved-complex [k][m] tiles (24 KB per stage, 96 KB per CTA, two CTAs per SM); fragment
+// an 8-stage ring of interleaved-complex [k][m] tiles (24.5 KB per stage, padded rows, one CTA per SM); fragment
 // loads are LDS.128 (a quarter warp reads 8 consecutive complex = 128 contiguous bytes: conflict free) and deliver
 // re and im together.  Per k8 step a warp issues 16 LDS.128 for 32 m16n8k8 MMAs (128 DMMA.884): 0.5 B of shared
 // traffic per FMA, 4x less than the 4x4 SIMT micro-tile of the generic kernel.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include "tnb_internal.h"
 
 namespace {
 
-constexpr int ZT_M = 128, ZT_N = 64, ZT_K = 8, ZT_THREADS = 512;
-constexpr int ZW_N = 2;     // n8 blocks per warp (warp tile 32 x 16 complex, 16 warps as 4 x 4)
+constexpr int ZT_K = 8;
+constexpr int ZW_N = 2;     // n8 blocks per warp (warp tile 32 x 16 complex)
+// CTA tile = WM x WN warps of 32 x 16 complex.  <4, 4>: 128 x 64, 512 threads, one CTA per SM — the throughput shape.
+// <2, 2>: 64 x 32, 128 threads, up to 4 CTAs per SM — for steps whose 128 x 64 grid (even split along K) cannot fill the
+// machine (configs[0]: 128 x 256 x 128 is 4 big tiles; a k-tile of a big tile occupies one SM's FP64 pipe for >= 4096
+// clocks whatever the rest of the chip does).
+template <int WM, int WN> struct ZCfg {
+    static constexpr int M = 32 * WM, N = 16 * WN, THREADS = 32 * WM * WN;
+    static constexpr int STAGES = (WM * WN >= 16) ? 8 : 4;             // consumed in pairs: one block barrier per two k-tiles
+    static constexpr int PA = M + 2, PB = N + 2;                        // padded row pitches (see below)
+    static constexpr int STAGE_ELEMS = (PA + PB) * ZT_K;
+    static constexpr int SMEM = STAGES * STAGE_ELEMS * 16;              // 196 KB / 50 KB
+    static constexpr int MIN_CTAS = (WM * WN >= 16) ? 1 : 3;             // 3 x 128 threads at <= 168 registers (4 would spill the loader state)
+};
 
 __device__ __forceinline__ int64_t ztab(const TabRef& t, uint32_t i) {
     uint32_t q = i / t.lo_size;
@@ -38,14 +51,11 @@ __device__ __forceinline__ void dmma16(double (&d)[4], const double (&a)[4], con
         : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
 }
 
-constexpr int ZT_STAGES = 4;
 // Row pitch of the shared tiles: +2 complex per k-row.  A fragment LDS.128 is served per quarter warp = lanes
 // (fr, fr+1) x (fk = 0..3), i.e. 4 different k-rows: with a pitch of 128 (or 64) elements all four rows start in the same
 // bank group (4-way conflict, ncu r2: 226 M conflicts, 41 % of the LSU wavefront budget); pitch = 2 (mod 8) elements puts
 // the eight 16-byte accesses of a quarter warp in eight different bank groups.
-constexpr int ZT_PA = ZT_M + 2, ZT_PB = ZT_N + 2;
-constexpr int ZT_STAGE_ELEMS = (ZT_PA + ZT_PB) * ZT_K;          // double2 elements per stage (24.5 KB)
-constexpr int ZT_SMEM = ZT_STAGES * ZT_STAGE_ELEMS * 16;        // 98 KB
+// (ZCfg::PA / PB)
 
 // sign flip on the integer pipe (x ^ sign bit): conj and the -Bim of Cre -= Aim.Bim must not cost FP64-pipe slots — DADD /
 // DMUL share the pipe the DMMAs run on
@@ -60,7 +70,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(ZT_THREADS, 1) einsum_c128_dmma_kernel(const EinsumArgs p) {
+template <int WM, int WN>
+__global__ void __launch_bounds__(ZCfg<WM, WN>::THREADS, ZCfg<WM, WN>::MIN_CTAS) einsum_c128_dmma_kernel(const EinsumArgs p) {
+    using Z = ZCfg<WM, WN>;
+    constexpr int ZT_M = Z::M, ZT_N = Z::N, ZT_THREADS = Z::THREADS, ZT_STAGES = Z::STAGES, ZT_PA = Z::PA, ZT_PB = Z::PB,
+                  ZT_STAGE_ELEMS = Z::STAGE_ELEMS;
     extern __shared__ __align__(16) double2 zsm[];               // [stage][ A: k x 128 | B: k x 64 ] interleaved complex
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -137,27 +151,38 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) einsum_c128_dmma_kernel(const E
 #pragma unroll
             for (int c = 0; c < 4; c++) { cre[i][j][c] = 0.; cim[i][j][c] = 0.; }
 
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * (8 * ZW_N);
+    const int wm = (warp % WM) * 32, wn = (warp / WM) * (8 * ZW_N);
     const int fr = lane >> 2, fk = lane & 3;     // fragment row group / k within a block
 
     const uint32_t ntiles = (k_end - k_begin + ZT_K - 1) / ZT_K;
-    // prologue: STAGES-1 tiles in flight (empty groups keep the accounting uniform)
+    // Tiles are loaded and consumed in PAIRS (one cp.async group and ONE __syncthreads per two k-tiles): right after a
+    // barrier all 16 warps are in their load phase and the FP64 pipe idles (ncu r2: 12.6 % barrier stalls, DMMA pipe 73 %);
+    // a pair per barrier halves that bubble without growing the per-thread loader state.
+    // prologue: 3 pairs in flight (empty groups keep the accounting uniform)
+    constexpr int ZT_PAIRS_AHEAD = ZT_STAGES / 2 - 1;
 #pragma unroll
-    for (int s = 0; s < ZT_STAGES - 1; s++) {
-        if ((uint32_t)s < ntiles) issue_tile(k_begin + s * ZT_K, s);
+    for (int g = 0; g < ZT_PAIRS_AHEAD; g++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if ((uint32_t)(2 * g + h) < ntiles) issue_tile(k_begin + (2 * g + h) * ZT_K, 2 * g + h);
         cp_async_commit();
     }
     for (uint32_t t = 0; t < ntiles; t++) {
-        cp_async_wait<ZT_STAGES - 2>();          // tile t has landed (for this thread's copies)
-        __syncthreads();                         // ... and for everybody's; also: everyone is done reading tile t-1
-        {
-            const uint32_t nt = t + ZT_STAGES - 1;
-            if (nt < ntiles) issue_tile(k_begin + nt * ZT_K, (int)(nt % ZT_STAGES));
+        if ((t & 1) == 0) {
+            cp_async_wait<ZT_PAIRS_AHEAD - 1>();     // pair t/2 has landed (for this thread's copies)
+            __syncthreads();                         // ... and for everybody's; also: everyone is done reading pair t/2 - 1
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t nt = t + 2 * ZT_PAIRS_AHEAD + h;
+                if (nt < ntiles) issue_tile(k_begin + nt * ZT_K, (int)(nt % ZT_STAGES));
+            }
             cp_async_commit();
         }
-        const double2* As = zsm + (t % ZT_STAGES) * ZT_STAGE_ELEMS;
-        const double2* Bs = As + ZT_PA * ZT_K;
+        const double2* As0 = zsm + (t % ZT_STAGES) * ZT_STAGE_ELEMS;
+        const double2* Bs0 = As0 + ZT_PA * ZT_K;
         {
+            const double2* As = As0;
+            const double2* Bs = Bs0;
             // A fragments for the whole warp tile (32 regs); B fragments one n8 block at a time (12 regs) so that
             // accumulators (64) + fragments fit the 128-register budget of two CTAs per SM.  The minus sign of
             // Cre -= Aim.Bim rides on the B fragment (-Bim).
@@ -247,18 +272,27 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) einsum_c128_dmma_kernel(const E
 // by s in {2, 3, 4} multiplies the CTA count; the s with the best wave efficiency is taken when it beats the unsplit grid
 // by more than the cost of the partial-sum pass (s x M x N elements written + read by the deterministic reducer).
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk,
-                           int64_t* ws_elems) {
+                           int64_t* ws_elems, int32_t* small_tiles) {
     *kchunk = K;
     *ws_elems = 0;
-    int64_t tiles = ((M + ZT_M - 1) / ZT_M) * ((N + ZT_N - 1) / ZT_N) * L;
     const int64_t sms = ctx ? ctx->sm_count : 148;
     const int64_t WS_MAX = (int64_t)1 << 24;
+    const int64_t tiles_big = ((M + 127) / 128) * ((N + 63) / 64) * L;
+    // small tiles when the 128 x 64 grid cannot fill the machine even with K split down to 32 per CTA
+    const bool small = tiles_big * std::max<int64_t>(1, K / 32) < sms;
+    if (small_tiles) *small_tiles = small ? 1 : 0;
+    const int64_t TM = small ? 64 : 128, TN = small ? 32 : 64;
+    int64_t tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN) * L;
     int64_t s = 1;
-    if (tiles < sms && K >= 128) {
+    if (small) {
+        if (K >= 32) {
+            const int64_t want = (3 * sms + tiles - 1) / tiles, maxs = K / 16;     // up to 3 small CTAs per SM
+            s = std::min(want, maxs);
+        }
+    } else if (tiles < sms && K >= 128) {
         int64_t want = (2 * sms + tiles - 1) / tiles;
         int64_t maxs = K / 32;
         s = want < maxs ? want : maxs;
-        while (s > 1 && s * M * N * L > WS_MAX) s--;
     } else if (tiles >= sms && tiles < 16 * sms && K >= 256) {
         auto eff = [&](int64_t c) { return (double)c / (double)(((c + sms - 1) / sms) * sms); };
         // time model per CTA-wave: K/s k-steps of the tile + the partial-sum traffic (s > 1): 3 x 16 B per element of C per split
@@ -271,6 +305,7 @@ int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
             if (e > best * 1.03) { best = e; s = c; }
         }
     }
+    while (s > 1 && s * M * N * L > 4 * WS_MAX) s--;
     if (s <= 1) return 1;
     int64_t kc = (K + s - 1) / s;
     kc = (kc + ZT_K - 1) / ZT_K * ZT_K;
@@ -281,18 +316,25 @@ int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
     return (int)s;
 }
 
-int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
-    int64_t tilesM = (a.M + ZT_M - 1) / ZT_M, tilesN = (a.N + ZT_N - 1) / ZT_N;
+template <int WM, int WN>
+static int launch_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
+    using Z = ZCfg<WM, WN>;
+    int64_t tilesM = (a.M + Z::M - 1) / Z::M, tilesN = (a.N + Z::N - 1) / Z::N;
     int64_t blocks = tilesM * tilesN * a.L * a.splitk;
     if (blocks <= 0) return TNB_OK;
     if (blocks >= ((int64_t)1 << 31)) return tnb_set_error(ctx, TNB_EUNSUPPORTED, "grid too large (%lld tiles)", (long long)blocks);
     static bool configured[16] = {false};
     if (!configured[ctx->device & 15]) {
-        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_c128_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZT_SMEM));
+        TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(einsum_c128_dmma_kernel<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z::SMEM));
         configured[ctx->device & 15] = true;
     }
-    einsum_c128_dmma_kernel<<<(unsigned)blocks, ZT_THREADS, ZT_SMEM, ctx->stream>>>(a);
+    einsum_c128_dmma_kernel<WM, WN><<<(unsigned)blocks, Z::THREADS, Z::SMEM, ctx->stream>>>(a);
     ctx->launches++;
     TNB_CUDA_CHECK(ctx, cudaGetLastError());
     return TNB_OK;
+}
+
+// a.pad_ = 1 selects the small-tile variant (decided by tnb_choose_splitk_dmma at plan time)
+int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
+    return a.pad_ ? launch_dmma<2, 2>(ctx, a) : launch_dmma<4, 4>(ctx, a);
 }

@@ -80,6 +80,7 @@ struct StepSpec {
     std::vector<int64_t> st_hi, st_rel, st_pos;
     size_t st_hi_pos = 0, st_rel_pos = 0, st_pos_pos = 0;
     bool kred = false;       // STREAM kernel variant: dense k-reduction kernel (small M x N, huge K)
+    int32_t dmma_small = 0;  // FP64 tensor-core kernel: 64 x 32 tiles (the 128 x 64 grid cannot fill the machine)
     int32_t tc_nt = 0;       // tcgen05 kernel: N tile (256/128), 0 = not used
     bool tc_swap = false;    // tcgen05 kernel: operands swapped (C^T = B A^T)
 };
@@ -178,7 +179,8 @@ int tnb_launch_c64_pair_staged(tnb_ctx* ctx, const StemArgs& e, int64_t Nsmall, 
 int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass);
 
 // kernels_c128_dmma.cu
-int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems);
+int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems,
+                           int32_t* small_tiles);
 int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a);
 
 // planner.cpp  (pure host code; also used by the dry-run plan that CPU tests inspect)

@@ -241,3 +241,58 @@ def binary_einsum(a: Tensor, b: Tensor, dims: Optional[Iterable[Hashable]] = Non
     sm = (C.c_int32 * max(len(dims), 1))(*[modes[i] for i in dims])
     check(ctx.handle, lib.tnb_binary_einsum(ctx.handle, C.byref(da), C.byref(db), C.byref(dc), sm, len(dims), None, None))
     return c
+
+
+def tensor_qr_thin(a: Tensor, inds_q: Sequence[Hashable], inds_r: Optional[Sequence[Hashable]] = None,
+                   ind_virtual: Hashable = "qr_virtual", ctx: Optional[Context] = None):
+    """Muscle.tensor_qr_thin(a; inds_q, inds_r, ind_virtual) on the device (canonize.jl:58): a = Q * R with
+    Q[inds_q..., ind_virtual] an isometry and R[ind_virtual, inds_r...]; the operand never leaves the GPU
+    (tnb_qr_thin: gather -> cuSOLVER geqrf/orgqr -> scatter)."""
+    ctx = ctx or default_context()
+    inds_q = list(inds_q)
+    inds_r = [i for i in a.inds if i not in inds_q] if inds_r is None else list(inds_r)
+    if set(inds_q) | set(inds_r) != set(a.inds) or set(inds_q) & set(inds_r) or ind_virtual in a.inds:
+        raise ValueError("inds_q / inds_r must partition the tensor's indices and ind_virtual must be new")
+    dt = _promote_dtype(a.dtype)
+    A = a.device(ctx, dt)
+    m = int(np.prod([a.size(i) for i in inds_q], dtype=np.int64)) if inds_q else 1
+    n = int(np.prod([a.size(i) for i in inds_r], dtype=np.int64)) if inds_r else 1
+    k = min(m, n)
+    q = Tensor(B200Array.empty([a.size(i) for i in inds_q] + [k], dt, ctx), tuple(inds_q) + (ind_virtual,))
+    r = Tensor(B200Array.empty([k] + [a.size(i) for i in inds_r], dt, ctx), (ind_virtual,) + tuple(inds_r))
+    modes = _mode_map(a.inds, [ind_virtual])
+    da, ka = _desc(a, A, modes)
+    dq, kq = _desc(q, q._dev, modes)
+    dr, kr = _desc(r, r._dev, modes)
+    # column order of the matrix view = the other modes in a's order; R is scattered into inds_r order by the descriptor
+    rows = (C.c_int32 * max(len(inds_q), 1))(*[modes[i] for i in inds_q])
+    check(ctx.handle, ctx.lib.tnb_qr_thin(ctx.handle, C.byref(da), rows, len(inds_q), modes[ind_virtual], C.byref(dq), C.byref(dr)))
+    return q, r
+
+
+def tensor_svd_thin(a: Tensor, inds_u: Sequence[Hashable], inds_v: Optional[Sequence[Hashable]] = None,
+                    ind_s: Hashable = "svd_virtual", ctx: Optional[Context] = None):
+    """Muscle.tensor_svd_thin(a; inds_u, inds_v, ind_s) on the device (canonize.jl:41,97; evolve.jl:62,92;
+    DMRG.jl:338,437): a = U * diag(s) * V with U[inds_u..., ind_s], s[ind_s] (real values in a's dtype, descending),
+    V[ind_s, inds_v...]."""
+    ctx = ctx or default_context()
+    inds_u = list(inds_u)
+    inds_v = [i for i in a.inds if i not in inds_u] if inds_v is None else list(inds_v)
+    if set(inds_u) | set(inds_v) != set(a.inds) or set(inds_u) & set(inds_v) or ind_s in a.inds:
+        raise ValueError("inds_u / inds_v must partition the tensor's indices and ind_s must be new")
+    dt = _promote_dtype(a.dtype)
+    A = a.device(ctx, dt)
+    m = int(np.prod([a.size(i) for i in inds_u], dtype=np.int64)) if inds_u else 1
+    n = int(np.prod([a.size(i) for i in inds_v], dtype=np.int64)) if inds_v else 1
+    k = min(m, n)
+    u = Tensor(B200Array.empty([a.size(i) for i in inds_u] + [k], dt, ctx), tuple(inds_u) + (ind_s,))
+    sv = Tensor(B200Array.empty([k], dt, ctx), (ind_s,))
+    v = Tensor(B200Array.empty([k] + [a.size(i) for i in inds_v], dt, ctx), (ind_s,) + tuple(inds_v))
+    modes = _mode_map(a.inds, [ind_s])
+    da, ka = _desc(a, A, modes)
+    du, ku = _desc(u, u._dev, modes)
+    ds, ks = _desc(sv, sv._dev, modes)
+    dv, kv = _desc(v, v._dev, modes)
+    rows = (C.c_int32 * max(len(inds_u), 1))(*[modes[i] for i in inds_u])
+    check(ctx.handle, ctx.lib.tnb_svd_thin(ctx.handle, C.byref(da), rows, len(inds_u), modes[ind_s], C.byref(du), C.byref(ds), C.byref(dv)))
+    return u, sv, v
