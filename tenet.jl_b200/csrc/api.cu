@@ -199,7 +199,7 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         if (S.splitk > 1 && ws) {
             a.splitk = S.splitk; a.kchunk = S.kchunk; a.ws = ws;
             int rc = tnb_launch_c128_dmma(ctx, a);
-            if (rc || (a.pad_ & 2)) return rc;        // bit 1: the kernel reduced its own partials (last CTA per tile)
+            if (rc) return rc;
             return tnb_launch_splitk_reduce(ctx, dtype, a);
         }
         return tnb_launch_c128_dmma(ctx, a);
@@ -355,11 +355,6 @@ static int plan_create_impl(tnb_ctx* ctx, const tnb_tensor* leaves, int32_t nlea
     P->info.table_bytes = (int64_t)(P->table_blob.size() * sizeof(int64_t));
     if (!dry) {
         cudaSetDevice(ctx->device);
-        for (const StepSpec& S : P->steps)
-            if (S.kernel == TNB_KERNEL_C128_DMMA && S.splitk > 1 && (S.dmma_small & 2)) {
-                if ((rc = tnb_dmma_ensure_counters(ctx))) { delete P; return rc; }
-                break;
-            }
         if (P->arena_elems > 0 && (rc = tnb_alloc(ctx, (size_t)P->arena_elems * esz, &P->arena))) { delete P; return rc; }
         if ((rc = tnb_alloc(ctx, std::max<size_t>(8, P->table_blob.size() * sizeof(int64_t)), &P->tables))) {
             tnb_free(ctx, P->arena); delete P; return rc;

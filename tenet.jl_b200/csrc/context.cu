@@ -65,7 +65,6 @@ int tnb_ctx_destroy(tnb_ctx* ctx) {
     tnb_comm_destroy(ctx);
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     ctx->free_blocks.clear();
-    if (ctx->dmma_counters) cudaFree(ctx->dmma_counters);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TNB_OK;

@@ -262,42 +262,6 @@ __global__ void __launch_bounds__(ZCfg<WM, WN>::THREADS, ZCfg<WM, WN>::MIN_CTAS)
                     }
                 }
         }
-    // Fused split-K reduction (p.pad_ bit 1): the LAST CTA of a tile to finish sums the partials of all splits in the fixed
-    // order ks = 0, 1, ... (deterministic, same order as the separate reducer kernel), applies alpha / beta and scatters the
-    // tile — one launch per step instead of two, which is what small latency-bound networks (configs[0]: 63 steps of a few
-    // microseconds) are made of.  The per-tile arrival counters live in a context-owned buffer (zeroed once) and are reset
-    // by the CTA that consumed them.
-    if (p.splitk > 1 && (p.pad_ & 2)) {
-        __shared__ int s_last;
-        int32_t* cnt = p.counters;
-        const uint32_t tile_id = (l * tilesN + bn) * tilesM + bm;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = atomicAdd(&cnt[tile_id], 1) == p.splitk - 1;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            double2* __restrict__ Cl = (double2*)p.C + ztab(p.cl, l);
-            for (int e = tid; e < ZT_M * ZT_N; e += ZT_THREADS) {
-                const uint32_t m = m0 + e % ZT_M, n = n0 + e / ZT_M;
-                if (m >= M || n >= N) continue;
-                double ar = 0., ai = 0.;
-                for (int sp = 0; sp < p.splitk; sp++) {
-                    const double2 v = W[(((uint64_t)l * p.splitk + sp) * N + n) * M + m];
-                    ar += v.x; ai += v.y;
-                }
-                double2 v = make_double2(p.alpha[0] * ar - p.alpha[1] * ai, p.alpha[0] * ai + p.alpha[1] * ar);
-                double2* dst = Cl + ztab(p.cm, m) + ztab(p.cn, n);
-                if (has_beta) {
-                    const double2 o = *dst;
-                    v.x += p.beta[0] * o.x - p.beta[1] * o.y;
-                    v.y += p.beta[0] * o.y + p.beta[1] * o.x;
-                }
-                *dst = v;
-            }
-            if (tid == 0) cnt[tile_id] = 0;
-        }
-    }
 }
 
 }  // namespace
@@ -349,8 +313,6 @@ int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
     if (s <= 1) return 1;
     *kchunk = kc;
     *ws_elems = s * M * N * L;
-    // fused reduction (last CTA of a tile sums the partials): whenever the arrival counters fit behind the partials
-    if (small_tiles && tiles <= TNB_DMMA_COUNTERS) *small_tiles |= 2;
     return (int)s;
 }
 
@@ -372,21 +334,7 @@ static int launch_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
     return TNB_OK;
 }
 
-// the context's arrival counters of the fused reduction (allocated and zeroed at first use)
-int tnb_dmma_ensure_counters(tnb_ctx* ctx) {
-    if (ctx->dmma_counters) return TNB_OK;
-    TNB_CUDA_CHECK(ctx, cudaMalloc(&ctx->dmma_counters, TNB_DMMA_COUNTERS * sizeof(int32_t)));
-    TNB_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dmma_counters, 0, TNB_DMMA_COUNTERS * sizeof(int32_t), ctx->stream));
-    return TNB_OK;
-}
-
-// a.pad_ bit 0 selects the small-tile variant, bit 1 the fused split-K reduction (both decided by tnb_choose_splitk_dmma)
-int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a0) {
-    EinsumArgs a = a0;
-    if (a.splitk > 1 && (a.pad_ & 2)) {
-        int rc = tnb_dmma_ensure_counters(ctx);   // no-op after plan creation (never inside a graph capture)
-        if (rc) return rc;
-        a.counters = (int32_t*)ctx->dmma_counters;
-    }
-    return (a.pad_ & 1) ? launch_dmma<2, 2>(ctx, a) : launch_dmma<4, 4>(ctx, a);
+// a.pad_ = 1 selects the small-tile variant (decided by tnb_choose_splitk_dmma at plan time)
+int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
+    return a.pad_ ? launch_dmma<2, 2>(ctx, a) : launch_dmma<4, 4>(ctx, a);
 }

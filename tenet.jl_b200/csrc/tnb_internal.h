@@ -42,9 +42,7 @@ struct EinsumArgs {
     int32_t pad_;
     int64_t kchunk;
     void* ws;
-    int32_t* counters;   // FP64 kernel, fused split-K reduction: per-tile arrival counters (context-owned, self-resetting)
 };
-constexpr int64_t TNB_DMMA_COUNTERS = 1 << 16;
 
 // host-side mirror of one group table
 struct HostTable {
@@ -114,7 +112,6 @@ struct tnb_ctx {
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
     int rank = 0, nranks = 1;
-    void* dmma_counters = nullptr;   // TNB_DMMA_COUNTERS int32 (kernels_c128_dmma.cu)
     void* multi = nullptr;   // tnb_multi: worker contexts + communicator of tnb_multi_contract_path (multi.cu)
 };
 void tnb_multi_release(tnb_ctx* ctx);
@@ -185,7 +182,6 @@ int64_t tnb_stem_tc_ws_elems(int64_t Nsmall, int64_t K, int64_t npass);
 int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t L, int64_t* kchunk, int64_t* ws_elems,
                            int32_t* small_tiles);
 int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a);
-int tnb_dmma_ensure_counters(tnb_ctx* ctx);
 
 // planner.cpp  (pure host code; also used by the dry-run plan that CPU tests inspect)
 struct PlanTensor {
