@@ -100,6 +100,19 @@ function Base.Array(d::B200Array{T,N}) where {T,N}
     return a
 end
 
+# Lazy conjugate: `conj(tensor)` on device storage is a FLAG (tnb_tensor.conj), not a copy — overlap.jl:7,39 and
+# DMRG.jl:80,96 materialise conj(ψ) on the CPU path; here the kernels conjugate at load time.
+struct ConjB200{T,N} <: AbstractArray{T,N}
+    parent::B200Array{T,N}
+end
+Base.size(a::ConjB200) = size(a.parent)
+Base.conj(a::B200Array{<:Complex}) = ConjB200(a)
+Base.conj(a::B200Array{<:Real}) = a
+Base.conj(a::ConjB200) = a.parent
+const B200Storage = Union{B200Array,ConjB200}
+storage(a::B200Array) = (a, false)
+storage(a::ConjB200) = (a.parent, true)
+
 Adapt.adapt_storage(::Type{B200Array}, a::Array) = upload(default_context(), a)
 Adapt.adapt_storage(::Type{Array}, a::B200Array) = Array(a)
 
@@ -124,6 +137,7 @@ struct Desc          # keeps the index arrays alive for the duration of a ccall
     keep::Tuple{Vector{Int64},Vector{Int64},Vector{Int32}}
 end
 
+Desc(a::ConjB200, labels::Vector{Int32}) = Desc(a.parent, labels; conj=true)
 function Desc(a::B200Array{T}, labels::Vector{Int32}; conj::Bool=false) where {T}
     e, s = collect(Int64, a.dims), collect(Int64, a.strides)
     Desc(TnbTensor(a.buf.h, a.offset, dtype_code(T), length(e), pointer(e), pointer(s), pointer(labels), conj), (e, s, labels))
@@ -134,7 +148,7 @@ label_map(indlists...) = (m = Dict{Any,Int32}(); for l in indlists, i in l; get!
 # --- Muscle.binary_einsum -----------------------------------------------------------------------------
 # semantics fixed by the reference's call sites: default contracts all shared inds (overlap.jl:42,46), dims=Index[]
 # keeps them as batch inds (canonize.jl:44, absorb.jl:31), rank-0 operands (DMRG.jl:60-61), rank-0 result (overlap.jl:49)
-function Muscle.binary_einsum(a::Tensor{T,N,<:B200Array}, b::Tensor{T,M,<:B200Array};
+function Muscle.binary_einsum(a::Tensor{T,N,<:B200Storage}, b::Tensor{T,M,<:B200Storage};
                               dims=intersect(inds(a), inds(b)), out=nothing) where {T,N,M}
     ia, ib = collect(inds(a)), collect(inds(b))
     free_a = [i for i in ia if i ∉ ib && i ∉ dims]
@@ -142,7 +156,7 @@ function Muscle.binary_einsum(a::Tensor{T,N,<:B200Array}, b::Tensor{T,M,<:B200Ar
     batch = [i for i in ia if i ∈ ib && i ∉ dims]
     ic = isnothing(out) ? vcat(free_a, free_b, batch) : collect(out)
     ext = merge(Dict(zip(ia, size(parent(a)))), Dict(zip(ib, size(parent(b)))))
-    c = B200Array{T}(undef, (ext[i] for i in ic)...; ctx=parent(a).buf.ctx)
+    c = B200Array{T}(undef, (ext[i] for i in ic)...; ctx=storage(parent(a))[1].buf.ctx)
     m = label_map(ia, ib)
     da = Desc(parent(a), Int32[m[i] for i in ia])
     db = Desc(parent(b), Int32[m[i] for i in ib])
@@ -157,12 +171,14 @@ function Muscle.binary_einsum(a::Tensor{T,N,<:B200Array}, b::Tensor{T,M,<:B200Ar
     return Tensor(c, ic)
 end
 
-# --- Tangles.contract ---------------------------------------------------------------------------------
-# post-order walk of the EinExpr tree -> SSA pairs; leaves are matched to tensors by their index sets
-function ssa_steps(path, leaf_of::Dict)
-    steps, next = Int32[], Ref(Int32(length(leaf_of)))
+# --- contract(tn; path) ---------------------------------------------------------------------------------
+# post-order walk of the EinExpr tree -> SSA pairs.  Leaves are matched to tensors by their index sets through a QUEUE
+# per set: two tensors carrying identical index sets are interchangeable in the tree (either assignment contracts the
+# same network), so they are handed out in order instead of colliding on one id (ADVICE r1).
+function ssa_steps(path, leaf_queue::Dict)
+    steps, next = Int32[], Ref(Int32(sum(length, values(leaf_queue); init=0)))
     function walk(node)
-        isempty(node.args) && return leaf_of[Set(node.head)]                  # [UPSTREAM-RECALL] EinExpr fields
+        isempty(node.args) && return popfirst!(leaf_queue[Set(node.head)])      # [UPSTREAM-RECALL] EinExpr fields
         ids = map(walk, node.args)
         acc = ids[1]
         for k in ids[2:end]
@@ -174,15 +190,22 @@ function ssa_steps(path, leaf_of::Dict)
     return steps
 end
 
-function Tangles.contract(tn::GenericTensorNetwork; path=einexpr(tn), sliced=Index[], kwargs...)
+# Own entry point (no method of Tangles.contract is overwritten — that would be type piracy): `TenetB200.contract(tn; ...)`.
+# The one-line dispatch a maintainer adds upstream is in INTEGRATION.md §3 (a storage trait on the tensors of the network).
+# `ngpus > 1` uses tnb_multi_contract_path: one host thread + context per device inside the library, slices dealt
+# round-robin, one NCCL all-reduce — the single Julia task never needs an external launcher (SURVEY §8b).
+function contract(tn; path=einexpr(tn), sliced=Index[], ngpus::Integer=1)
     ts = collect(tensors(tn))
-    all(t -> parent(t) isa B200Array, ts) || return invoke(Tangles.contract, Tuple{Any}, tn; path, kwargs...)
+    all(t -> parent(t) isa B200Storage, ts) || throw(ArgumentError("TenetB200.contract needs device-resident tensors: adapt(B200Array, tn) first"))
     T = eltype(parent(ts[1]))
-    ctx = parent(ts[1]).buf.ctx
+    ctx = storage(parent(ts[1]))[1].buf.ctx
     m = label_map((inds(t) for t in ts)...)
     descs = [Desc(parent(t), Int32[m[i] for i in inds(t)]) for t in ts]
-    leaf_of = Dict(Set(inds(t)) => Int32(k - 1) for (k, t) in enumerate(ts))
-    steps = ssa_steps(path, leaf_of)
+    leaf_queue = Dict{Any,Vector{Int32}}()
+    for (k, t) in enumerate(ts)
+        push!(get!(leaf_queue, Set(inds(t)), Int32[]), Int32(k - 1))
+    end
+    steps = ssa_steps(path, leaf_queue)
     iout = collect(path.head)
     ext = Dict(i => size(t, i) for t in ts for i in inds(t))
     out = B200Array{T}(undef, (ext[i] for i in iout)...; ctx)
@@ -191,12 +214,55 @@ function Tangles.contract(tn::GenericTensorNetwork; path=einexpr(tn), sliced=Ind
     nslices = prod((ext[i] for i in sliced); init=1)
     raw = [d.t for d in descs]
     GC.@preserve descs dout steps sm raw begin
-        check(ctx, @ccall lib.tnb_contract_path(ctx.h::Ptr{Cvoid}, raw::Ptr{TnbTensor}, length(raw)::Int32,
-                                                steps::Ptr{Int32}, (length(steps) ÷ 2)::Int32, sm::Ptr{Int32},
-                                                length(sm)::Int32, 0::Int64, 1::Int64, nslices::Int64,
-                                                Ref(dout.t)::Ptr{TnbTensor})::Cint)
+        if ngpus > 1
+            check(ctx, @ccall lib.tnb_multi_contract_path(ctx.h::Ptr{Cvoid}, raw::Ptr{TnbTensor}, length(raw)::Int32,
+                                                          steps::Ptr{Int32}, (length(steps) ÷ 2)::Int32, sm::Ptr{Int32},
+                                                          length(sm)::Int32, Ref(dout.t)::Ptr{TnbTensor}, ngpus::Int32)::Cint)
+        else
+            check(ctx, @ccall lib.tnb_contract_path(ctx.h::Ptr{Cvoid}, raw::Ptr{TnbTensor}, length(raw)::Int32,
+                                                    steps::Ptr{Int32}, (length(steps) ÷ 2)::Int32, sm::Ptr{Int32},
+                                                    length(sm)::Int32, 0::Int64, 1::Int64, nslices::Int64,
+                                                    Ref(dout.t)::Ptr{TnbTensor})::Cint)
+        end
     end
     return Tensor(out, iout)
+end
+
+# --- Muscle.tensor_qr_thin / tensor_svd_thin on device storage (canonize.jl:41,58,97; evolve.jl:62,92; DMRG.jl:338,437) ---
+function Muscle.tensor_qr_thin(a::Tensor{T,N,<:B200Storage}; inds_q, inds_r=setdiff(inds(a), inds_q), ind_virtual) where {T,N}
+    ia = collect(inds(a))
+    ext = Dict(zip(ia, size(parent(a))))
+    k = min(prod((ext[i] for i in inds_q); init=1), prod((ext[i] for i in inds_r); init=1))
+    ctx = storage(parent(a))[1].buf.ctx
+    q = B200Array{T}(undef, (ext[i] for i in inds_q)..., k; ctx)
+    r = B200Array{T}(undef, k, (ext[i] for i in inds_r)...; ctx)
+    m = label_map(ia, [ind_virtual])
+    da = Desc(parent(a), Int32[m[i] for i in ia])
+    dq = Desc(q, Int32[[m[i] for i in inds_q]; m[ind_virtual]])
+    dr = Desc(r, Int32[m[ind_virtual]; [m[i] for i in inds_r]])
+    rows = Int32[m[i] for i in inds_q]
+    GC.@preserve da dq dr rows check(ctx, @ccall lib.tnb_qr_thin(ctx.h::Ptr{Cvoid}, Ref(da.t)::Ptr{TnbTensor}, rows::Ptr{Int32},
+        length(rows)::Int32, m[ind_virtual]::Int32, Ref(dq.t)::Ptr{TnbTensor}, Ref(dr.t)::Ptr{TnbTensor})::Cint)
+    return Tensor(q, [collect(inds_q); ind_virtual]), Tensor(r, [ind_virtual; collect(inds_r)])
+end
+
+function Muscle.tensor_svd_thin(a::Tensor{T,N,<:B200Storage}; inds_u, inds_v=setdiff(inds(a), inds_u), ind_s) where {T,N}
+    ia = collect(inds(a))
+    ext = Dict(zip(ia, size(parent(a))))
+    k = min(prod((ext[i] for i in inds_u); init=1), prod((ext[i] for i in inds_v); init=1))
+    ctx = storage(parent(a))[1].buf.ctx
+    u = B200Array{T}(undef, (ext[i] for i in inds_u)..., k; ctx)
+    sv = B200Array{T}(undef, k; ctx)
+    v = B200Array{T}(undef, k, (ext[i] for i in inds_v)...; ctx)
+    m = label_map(ia, [ind_s])
+    da = Desc(parent(a), Int32[m[i] for i in ia])
+    du = Desc(u, Int32[[m[i] for i in inds_u]; m[ind_s]])
+    ds = Desc(sv, Int32[m[ind_s]])
+    dv = Desc(v, Int32[m[ind_s]; [m[i] for i in inds_v]])
+    rows = Int32[m[i] for i in inds_u]
+    GC.@preserve da du ds dv rows check(ctx, @ccall lib.tnb_svd_thin(ctx.h::Ptr{Cvoid}, Ref(da.t)::Ptr{TnbTensor}, rows::Ptr{Int32},
+        length(rows)::Int32, m[ind_s]::Int32, Ref(du.t)::Ptr{TnbTensor}, Ref(ds.t)::Ptr{TnbTensor}, Ref(dv.t)::Ptr{TnbTensor})::Cint)
+    return Tensor(u, [collect(inds_u); ind_s]), Tensor(sv, [ind_s]), Tensor(v, [ind_s; collect(inds_v)])
 end
 
 end # module

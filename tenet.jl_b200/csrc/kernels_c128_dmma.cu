@@ -8,7 +8,8 @@
 //   any rank / strides / batch / conj, ragged edges by predication, split-K partials to a workspace)
 //
 // Complex from real DMMAs:  Cre += Are.Bre + (-Aim).Bim ;  Cim += Are.Bim + Aim.Bre  (4 DMMAs per 8x8x4 complex block).
-// CTA tile 128(m) x 64(n) x 8(k), 256 threads = 8 warps as 4(m) x 2(n), warp tile 32 x 32 complex = 64 accumulator
+// CTA tile (ZCfg below; default 64(m) x 64(n) x 8(k), 256 threads = 8 warps as 2(m) x 4(n), two CTAs per SM), warp tile
+// 32 x 16 complex = 64 accumulator
 // registers per thread.  Operands go global -> shared with cp.async (16 B = one complex, zero-fill at ragged edges) into
 // an 8-stage ring of interleaved-complex [k][m] tiles (24.5 KB per stage, padded rows, one CTA per SM); fragment
 // loads are LDS.128 (a quarter warp reads 8 consecutive complex = 128 contiguous bytes: conflict free) and deliver
@@ -16,6 +17,7 @@
 // traffic per FMA, 4x less than the 4x4 SIMT micro-tile of the generic kernel.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <stdint.h>
 #include "tnb_internal.h"
 
@@ -29,11 +31,11 @@ constexpr int ZW_N = 2;     // n8 blocks per warp (warp tile 32 x 16 complex)
 // clocks whatever the rest of the chip does).
 template <int WM, int WN> struct ZCfg {
     static constexpr int M = 32 * WM, N = 16 * WN, THREADS = 32 * WM * WN;
-    static constexpr int STAGES = (WM * WN >= 16) ? 8 : 4;             // consumed in pairs: one block barrier per two k-tiles
+    static constexpr int STAGES = (WM * WN >= 16) ? 8 : (WM * WN == 8 ? 6 : 4);   // consumed in pairs: one block barrier per two k-tiles
     static constexpr int PA = M + 2, PB = N + 2;                        // padded row pitches (see below)
     static constexpr int STAGE_ELEMS = (PA + PB) * ZT_K;
     static constexpr int SMEM = STAGES * STAGE_ELEMS * 16;              // 196 KB / 50 KB
-    static constexpr int MIN_CTAS = (WM * WN >= 16) ? 1 : 3;             // 3 x 128 threads at <= 168 registers (4 would spill the loader state)
+    static constexpr int MIN_CTAS = (WM * WN >= 16) ? 1 : (WM * WN == 8 ? 2 : 3);             // 3 x 128 threads at <= 168 registers (4 would spill the loader state)
 };
 
 __device__ __forceinline__ int64_t ztab(const TabRef& t, uint32_t i) {
@@ -281,20 +283,21 @@ int tnb_choose_splitk_dmma(const tnb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
     // small tiles when the 128 x 64 grid cannot fill the machine even with K split down to 32 per CTA
     const bool small = tiles_big * std::max<int64_t>(1, K / 32) < sms;
     if (small_tiles) *small_tiles = small ? 1 : 0;
-    const int64_t TM = small ? 64 : 128, TN = small ? 32 : 64;
+    const int64_t TM = 64, TN = small ? 32 : 64;
     int64_t tiles = ((M + TM - 1) / TM) * ((N + TN - 1) / TN) * L;
+    const int64_t slots = (small ? 3 : 2) * sms;                        // resident CTAs
     int64_t s = 1;
     if (small) {
         if (K >= 32) {
-            const int64_t want = (3 * sms + tiles - 1) / tiles, maxs = K / 16;     // up to 3 small CTAs per SM
+            const int64_t want = (slots + tiles - 1) / tiles, maxs = K / 16;
             s = std::min(want, maxs);
         }
-    } else if (tiles < sms && K >= 128) {
-        int64_t want = (2 * sms + tiles - 1) / tiles;
+    } else if (tiles < slots && K >= 128) {
+        int64_t want = (2 * slots + tiles - 1) / tiles;
         int64_t maxs = K / 32;
         s = want < maxs ? want : maxs;
-    } else if (tiles >= sms && tiles < 16 * sms && K >= 256) {
-        auto eff = [&](int64_t c) { return (double)c / (double)(((c + sms - 1) / sms) * sms); };
+    } else if (tiles >= slots && tiles < 16 * slots && K >= 256) {
+        auto eff = [&](int64_t c) { return (double)c / (double)(((c + slots - 1) / slots) * slots); };
         // time model per CTA-wave: K/s k-steps of the tile + the partial-sum traffic (s > 1): 3 x 16 B per element of C per split
         // against ~8 K flops per element at the kernel's rate; expressed as a fraction of the unsplit runtime
         double best = eff(tiles);
@@ -336,5 +339,10 @@ static int launch_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
 
 // a.pad_ = 1 selects the small-tile variant (decided by tnb_choose_splitk_dmma at plan time)
 int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
-    return a.pad_ ? launch_dmma<2, 2>(ctx, a) : launch_dmma<4, 4>(ctx, a);
+    if (a.pad_) return launch_dmma<2, 2>(ctx, a);
+    // Default: 64 x 64 tiles, 256 threads, TWO CTAs per SM.  Two independent CTAs fill each other's barrier / load bubbles:
+    // measured 29.9 vs 26.0 TFLOP/s (configs[4]) and 28.9 vs 25.9 (configs[3]) against the one-CTA 128 x 64 form, which
+    // TNB_DMMA_TILE=0 still selects (comparison).
+    static const int medium = [] { const char* e = getenv("TNB_DMMA_TILE"); return e ? atoi(e) : 1; }();
+    return medium ? launch_dmma<2, 4>(ctx, a) : launch_dmma<4, 4>(ctx, a);
 }

@@ -153,14 +153,20 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
     if (per_sm > by_threads) per_sm = by_threads;
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
-    int64_t grid = (int64_t)ctx->sm_count * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    if (grid < 1) return TNB_OK;
+    // persistent grid = what is actually RESIDENT (registers and shared memory decide): a grid sized from shared memory
+    // alone left CTAs queued behind the resident ones and the kernel ran in 2.3 "waves" with an idle tail (r2)
 #define ST_LAUNCH(NMAX)                                                                                            \
     do {                                                                                                           \
         if (smem > 48 * 1024)                                                                                      \
             TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(stem_kernel<E, VM, NMAX>,                                     \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        int resident = 0;                                                                                          \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, stem_kernel<E, VM, NMAX>, threads, smem) ==   \
+                cudaSuccess && resident >= 1 && resident < per_sm)                                                 \
+            per_sm = resident;                                                                                     \
+        int64_t grid = (int64_t)ctx->sm_count * per_sm;                                                            \
+        if (grid > ntiles) grid = ntiles;                                                                          \
+        if (grid < 1) return TNB_OK;                                                                               \
         stem_kernel<E, VM, NMAX><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);                            \
     } while (0)
     if (a.N <= 4) ST_LAUNCH(4);
