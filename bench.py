@@ -586,6 +586,10 @@ def main():
                 full["rel_diff_vs_golden_n1"] = rel
                 full["bound"] = C64_AMPLITUDE_BOUND
                 full["within_bound"] = bool(rel <= C64_AMPLITUDE_BOUND)
+                if "amplitude_c128" in gold:     # the complex128 truth (same engine, FP64 kernels, tools/full_amplitude.py --dtype c128)
+                    t128 = complex(*gold["amplitude_c128"])
+                    full["rel_err_vs_c128_truth"] = abs(z - t128) / abs(t128)
+                    full["within_bound"] = bool(full["within_bound"] and full["rel_err_vs_c128_truth"] <= C64_AMPLITUDE_BOUND)
 
     total_slices, total_flops = r.work(a.steps)
     value = total_flops / (ms * 1e-3) / 1e12

@@ -344,5 +344,6 @@ int tnb_launch_c128_dmma(tnb_ctx* ctx, const EinsumArgs& a) {
     // measured 29.9 vs 26.0 TFLOP/s (configs[4]) and 28.9 vs 25.9 (configs[3]) against the one-CTA 128 x 64 form, which
     // TNB_DMMA_TILE=0 still selects (comparison).
     static const int medium = [] { const char* e = getenv("TNB_DMMA_TILE"); return e ? atoi(e) : 1; }();
+    if (medium == 2) return launch_dmma<2, 2>(ctx, a);     // experiment: 64 x 32 tiles, three CTAs per SM
     return medium ? launch_dmma<2, 4>(ctx, a) : launch_dmma<4, 4>(ctx, a);
 }
