@@ -850,6 +850,8 @@ struct StemTcArgs {
     int32_t run_shift;        // log2 of the contiguous output run length; run bases are rel[j << run_shift]
     int32_t additive;         // pos[row*N + col] == pos[row*N] + pos[col] - pos[0]
     int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
+    int32_t egroups;          // epilogue groups: 2 = two groups of 4 warps with one TMEM set + one staging tile each (two tiles in
+                              // flight in the epilogue), 1 = one group of 8 warps
     int32_t off_stg, off_tab, off_run, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
     int64_t brep_stride;      // streamed-B mode: byte distance between the SK_BREP replicas of the pre-split planes
     const uint8_t* bplanes;   // streamed-B mode: pre-split planes of this pass in global memory, [kb][hi|lo][2*NT rows x 32 B]
@@ -866,7 +868,7 @@ __host__ inline int sk_layout(int nt, StemTcArgs& a) {
     const int nkb = a.K / TC_BK;
     const int nruns = (TC_BM * a.N) >> a.run_shift;
     a.off_stg = up((a.bplanes ? (nt == 128 ? SK_BST / 2 : SK_BST) : nkb) * nt * 128, 1024);
-    a.off_tab = a.off_stg + up(TC_BM * a.N * 8, 1024);
+    a.off_tab = a.off_stg + a.egroups * up(TC_BM * a.N * 8, 1024);
     a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
     a.off_raw = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
     int raw = (SK_BUDGET - (SK_NBARS * 8 + 16) - a.off_raw) / SK_RAW_STAGE;
@@ -939,7 +941,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     if (tid == 0) {
         for (int s = 0; s < SK_RAW; s++) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), SK_WORKERS / 64); }
         for (int s = 0; s < SK_PL_MAX; s++) { mbar_init(apl_full(s), SK_WORKERS / 64); mbar_init(apl_empty(s), 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32); }
+        for (int s = 0; s < 2; s++) { mbar_init(accfull_bar(s), 1); mbar_init(accempty_bar(s), SK_EPI / 32 / p.egroups); }
         for (int s = 0; s < BST; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1019,21 +1021,28 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         }
     } else if (warp < 16) {
         // ---- epilogue warps: TMEM -> (combine) -> staging (rank order) -> C (ascending addresses) ----
-        const int q = warp & 3, half = (warp - 8) >> 2;
-        const int etid = tid - SK_WORKERS;                         // 0..255
+        // Two epilogue GROUPS (p.egroups == 2, forms with two TMEM sets): warps 8-11 take the even tiles of this CTA (set 0,
+        // staging tile 0), warps 12-15 the odd ones, each warp draining ALL columns of its lane quarter — the drain + staging
+        // of one tile overlaps the write-out of the previous one (one group: drain -> write-out was a serial chain per tile,
+        // the limiter of the write-heavy small steps, r1 verdict).  One group (p.egroups == 1): 8 warps, two per lane quarter.
+        const int G = p.egroups, EG = SK_EPI / G;                   // threads per group
+        const int grp = G == 2 ? (warp - 8) >> 2 : 0;
+        const int q = warp & 3, half = G == 2 ? 0 : (warp - 8) >> 2;
+        const int etid = tid - SK_WORKERS - grp * EG;              // 0..EG-1
         const uint32_t row = q * 32 + lane;
-        float2* stg = reinterpret_cast<float2*>(smem + p.off_stg);
+        const int stg_bytes = (TC_BM * p.N * 8 + 1023) / 1024 * 1024;
+        float2* stg = reinterpret_cast<float2*>(smem + p.off_stg + grp * stg_bytes);
         const bool has_beta = p.beta[0] != 0.f || p.beta[1] != 0.f;
         const float ar = p.alpha[0], ai = p.alpha[1], br = p.beta[0], bi = p.beta[1];
         const bool unit_alpha = ar == 1.f && ai == 0.f;
         const int cnt = TC_BM * p.N;
-        constexpr int COLS = NT >= 32 ? NT / 2 : NT;               // columns per warp (NT = 16: warps of half 1 skip the drain)
-        const int cbeg = NT >= 32 ? half * COLS : 0;
+        const int COLS = (NT >= 32 && G == 1) ? NT / 2 : NT;       // columns per warp (NT = 16, one group: warps of half 1 skip the drain)
+        const int cbeg = (NT >= 32 && G == 1) ? half * COLS : 0;
         const bool drains = NT >= 32 || half == 0;
         const bool additive = p.additive != 0;
         // additive: this thread's row contributes a fixed (swizzled) byte offset
         const uint32_t rowoff = additive ? 8u * sk_swz((uint32_t)p.pos[(int64_t)row * p.N]) : 0u;
-        uint8_t* stg_b = smem + p.off_stg;
+        uint8_t* stg_b = smem + p.off_stg + grp * stg_bytes;
         const int rmask = (1 << p.run_shift) - 1;
         const int cend = (cbeg + COLS) < p.N ? (cbeg + COLS) : p.N;   // N is a multiple of 16 (eligibility)
         // write-out: pair j = 2*etid + 512*it; swz is XOR-linear and the two parts use disjoint bits
@@ -1042,11 +1051,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         uint32_t i = 0;
         uint32_t echunk0 = 0, echunk1 = 0;                          // chunks drained so far, per accumulator set
         const uint32_t nchunks = (nkb + SK_KCB - 1) / SK_KCB;
-        int64_t hi_next = blockIdx.x < ntiles ? p.hi[blockIdx.x] : 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, i++) {
+        const int64_t t0 = blockIdx.x + (int64_t)grp * gridDim.x, tstep = (int64_t)G * gridDim.x;
+        int64_t hi_next = t0 < ntiles ? p.hi[t0] : 0;
+        i = (uint32_t)grp;
+        for (int64_t t = t0; t < ntiles; t += tstep, i += (uint32_t)G) {
             const uint32_t set = i % NSETS;
             const int64_t hi_cur = hi_next;
-            if (t + gridDim.x < ntiles) hi_next = p.hi[t + gridDim.x];   // in flight while this tile drains
+            if (t + tstep < ntiles) hi_next = p.hi[t + tstep];          // in flight while this tile drains
             // K > 128 (128-column form only): the accumulators hold one chunk of SK_KCB k-blocks at a time; chunk 0 is
             // stored into the staging tile, later chunks are added to it round-to-nearest (each thread owns its entries)
             for (uint32_t ch = 0; ch < nchunks; ch++) {
@@ -1105,20 +1116,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
             __syncwarp();
             if (lane == 0) mbar_arrive(accempty_bar(set));          // TMEM set free: the next chunk / tile may start
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile complete (epilogue warps only)
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(EG) : "memory");   // staging tile complete (this group's warps only)
             float2* base = p.C + hi_cur;
             if (p.vec2) {
                 constexpr int U = 4;                                 // pairs in flight per thread; cnt is a multiple of 2048
-                for (int j0 = etid * 2; j0 < cnt; j0 += 2 * SK_EPI * U) {
+                for (int j0 = etid * 2; j0 < cnt; j0 += 2 * EG * U) {
                     float4 w[U];
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const uint32_t s = swz_t ^ sk_swz((uint32_t)(j0 - etid * 2 + u * 2 * SK_EPI));
+                        const uint32_t s = swz_t ^ sk_swz((uint32_t)(j0 - etid * 2 + u * 2 * EG));
                         w[u] = *reinterpret_cast<const float4*>(stg + (s & ~1u));
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const int j = j0 + u * 2 * SK_EPI;
+                        const int j = j0 + u * 2 * EG;
                         float2 v0 = odd ? make_float2(w[u].z, w[u].w) : make_float2(w[u].x, w[u].y);
                         float2 v1 = odd ? make_float2(w[u].x, w[u].y) : make_float2(w[u].z, w[u].w);
                         if (!unit_alpha) {
@@ -1138,7 +1149,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 }
             } else {
 #pragma unroll 4
-                for (int j = etid; j < cnt; j += SK_EPI) {
+                for (int j = etid; j < cnt; j += EG) {
                     float2 v = stg[sk_swz((uint32_t)j)];
                     float2 o = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
                     const int run = j >> p.run_shift;
@@ -1152,7 +1163,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                     *dst = o;
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // staging tile free again
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(EG) : "memory");   // staging tile free again
         }
     } else if (warp == 16) {
         // ---- MMA issuer: A planes from tensor memory, B planes from shared memory.  The whole warp runs the loop
@@ -1275,6 +1286,11 @@ __global__ void stem_bsplit_kernel(const float2* __restrict__ B, TabRef bn, TabR
 
 template <int NT, bool BSTREAM, bool WIDE64 = false>
 int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
+    // two epilogue groups whenever the form has two TMEM sets and the second staging tile leaves >= 6 raw stages
+    // (TNB_STEM_EGROUPS=1: one group, comparison)
+    static const int eg_env = [] { const char* e = getenv("TNB_STEM_EGROUPS"); return e ? atoi(e) : 2; }();
+    a.egroups = (NT <= 64 && !WIDE64 && eg_env == 2) ? 2 : 1;
+    if (a.egroups == 2 && sk_layout(NT, a) < 6) a.egroups = 1;
     if (sk_layout(NT, a) < 3) return -1;
     const int smem = a.off_bar + SK_NBARS * 8 + 16;
     TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(c64_tf32x3_stem_kernel<NT, BSTREAM, WIDE64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_BUDGET));
