@@ -1047,7 +1047,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         const int cend = (cbeg + COLS) < p.N ? (cbeg + COLS) : p.N;   // N is a multiple of 16 (eligibility)
         // write-out: pair j = 2*etid + 512*it; swz is XOR-linear and the two parts use disjoint bits
         const uint32_t swz_t = sk_swz((uint32_t)etid * 2u);
-        const bool odd = (swz_t & 1u) != 0;                         // pair stored in swapped order (thread constant)
         uint32_t i = 0;
         uint32_t echunk0 = 0, echunk1 = 0;                          // chunks drained so far, per accumulator set
         const uint32_t nchunks = (nkb + SK_KCB - 1) / SK_KCB;
@@ -1122,16 +1121,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
                 constexpr int U = 4;                                 // pairs in flight per thread; cnt is a multiple of 2048
                 for (int j0 = etid * 2; j0 < cnt; j0 += 2 * EG * U) {
                     float4 w[U];
+                    bool od[U];                                      // pair stored in swapped order: bit 0 of the swizzled rank.  With
+                                                                     // 256 threads it is a thread constant (offsets are multiples of
+                                                                     // 512); with two groups of 128 the 256-offsets flip it
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const uint32_t s = swz_t ^ sk_swz((uint32_t)(j0 - etid * 2 + u * 2 * EG));
                         w[u] = *reinterpret_cast<const float4*>(stg + (s & ~1u));
+                        od[u] = (s & 1u) != 0;
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int j = j0 + u * 2 * EG;
-                        float2 v0 = odd ? make_float2(w[u].z, w[u].w) : make_float2(w[u].x, w[u].y);
-                        float2 v1 = odd ? make_float2(w[u].x, w[u].y) : make_float2(w[u].z, w[u].w);
+                        float2 v0 = od[u] ? make_float2(w[u].z, w[u].w) : make_float2(w[u].x, w[u].y);
+                        float2 v1 = od[u] ? make_float2(w[u].x, w[u].y) : make_float2(w[u].z, w[u].w);
                         if (!unit_alpha) {
                             v0 = make_float2(ar * v0.x - ai * v0.y, ar * v0.y + ai * v0.x);
                             v1 = make_float2(ar * v1.x - ai * v1.y, ar * v1.y + ai * v1.x);
