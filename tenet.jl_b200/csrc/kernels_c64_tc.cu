@@ -852,6 +852,8 @@ struct StemTcArgs {
     int32_t vec2;             // run >= 2, every run base even, C 16-byte aligned: the write-out moves pairs
     int32_t egroups;          // epilogue groups: 2 = two groups of 4 warps with one TMEM set + one staging tile each (two tiles in
                               // flight in the epilogue), 1 = one group of 8 warps
+    int32_t direct;           // epilogue stores rows straight from registers (one column of 32 consecutive rows per warp
+                              // instruction fills whole sectors — planner.cpp st_direct): no staging tile, no rank tables
     int32_t off_stg, off_tab, off_run, off_raw, off_bar;   // shared-memory map (bytes), B planes at 0
     int64_t brep_stride;      // streamed-B mode: byte distance between the SK_BREP replicas of the pre-split planes
     const uint8_t* bplanes;   // streamed-B mode: pre-split planes of this pass in global memory, [kb][hi|lo][2*NT rows x 32 B]
@@ -868,9 +870,9 @@ __host__ inline int sk_layout(int nt, StemTcArgs& a) {
     const int nkb = a.K / TC_BK;
     const int nruns = (TC_BM * a.N) >> a.run_shift;
     a.off_stg = up((a.bplanes ? (nt == 128 ? SK_BST / 2 : SK_BST) : nkb) * nt * 128, 1024);
-    a.off_tab = a.off_stg + a.egroups * up(TC_BM * a.N * 8, 1024);
-    a.off_run = a.off_tab + up(a.additive ? nt * 4 : TC_BM * a.N * 2, 16);
-    a.off_raw = up(a.off_run + (nruns <= SK_RUNS_MAX ? nruns * 4 : 0), 1024);
+    a.off_tab = a.off_stg + (a.direct ? 0 : a.egroups * up(TC_BM * a.N * 8, 1024));
+    a.off_run = a.off_tab + up((a.additive || a.direct) ? nt * 4 : TC_BM * a.N * 2, 16);
+    a.off_raw = up(a.off_run + ((nruns <= SK_RUNS_MAX && !a.direct) ? nruns * 4 : 0), 1024);
     int raw = (SK_BUDGET - (SK_NBARS * 8 + 16) - a.off_raw) / SK_RAW_STAGE;
     if (raw > SK_RAW_MAX) raw = SK_RAW_MAX;
     a.raw_stages = raw;
@@ -957,7 +959,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         }
         split_store_b(smem + kb * B_KB, (int)b_plane, NT, (int)row, (int)kc, v, p.conjB);
     }
-    if (p.additive) {
+    if (p.direct) {
+        // column address deltas (the address of (row, col) is rel[pos[row*N]] + (rel[pos[col]] - rel[pos[0]]))
+        int32_t* coltab = reinterpret_cast<int32_t*>(smem + p.off_tab);
+        const int64_t a0 = p.rel[p.pos[0]];
+        for (int i = tid; i < NT; i += SK_THREADS) coltab[i] = i < p.N ? (int32_t)(p.rel[p.pos[i]] - a0) : 0;
+    } else if (p.additive) {
         // separable rank on disjoint bits: staging byte offset of (row, col) = rowoff ^ coloff (the swizzle is XOR-linear)
         const int64_t p0 = p.pos[0];
         for (int i = tid; i < NT; i += SK_THREADS) tab32[i] = i < p.N ? 8u * sk_swz((uint32_t)(p.pos[i] - p0)) : 0u;
@@ -970,7 +977,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
     }
     {
         int big = 0;
-        if (runs_in_smem)
+        if (runs_in_smem && !p.direct)
             for (int i = tid; i < nruns; i += SK_THREADS) {
                 const int64_t v = p.rel[(int64_t)i << p.run_shift];
                 if (v < 0 || v >= ((int64_t)1 << 31)) big = 1;
@@ -1053,6 +1060,68 @@ __global__ void __launch_bounds__(SK_THREADS, 1) c64_tf32x3_stem_kernel(const St
         const int64_t t0 = blockIdx.x + (int64_t)grp * gridDim.x, tstep = (int64_t)G * gridDim.x;
         int64_t hi_next = t0 < ntiles ? p.hi[t0] : 0;
         i = (uint32_t)grp;
+        if (p.direct) {
+            // ---- direct epilogue: TMEM -> registers -> C.  A thread owns one row; a warp instruction stores one column of
+            // 32 consecutive rows, which the planner has checked to fill whole 32-byte sectors.  No staging tile, no group
+            // barrier: the shared-memory pipe carries only the raw A tiles (it was the limiter of these steps: 64-72 % busy
+            // with the staging round trip, profiles/r2_ncu_stalls.md) and each warp runs on its own. ----
+            const int32_t* coltab = reinterpret_cast<const int32_t*>(smem + p.off_tab);
+            const int64_t rowaddr = p.rel[p.pos[(int64_t)row * p.N]];
+            for (int64_t t = t0; t < ntiles; t += tstep, i += (uint32_t)G) {
+                const uint32_t set = i % NSETS;
+                const int64_t hi_cur = hi_next;
+                if (t + tstep < ntiles) hi_next = p.hi[t + tstep];
+                mbar_wait(accfull_bar(set), (set ? echunk1 : echunk0) & 1);
+                if (set) echunk1++; else echunk0++;
+                tc_fence_after();
+                if (drains) {
+                    float2* rbase = p.C + hi_cur + rowaddr;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * SET_COLS;
+#pragma unroll 1
+                    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                        uint32_t xr[16], xi[16];
+                        if (F6) {
+                            uint32_t er[16], ei[16];
+                            tmem_ld16(taddr + c0, xr);
+                            tmem_ld16(taddr + NT + c0, xi);
+                            tmem_ld16(taddr + 2 * NT + c0, er);
+                            tmem_ld16(taddr + 3 * NT + c0, ei);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                xr[j] = __float_as_uint(__uint_as_float(xr[j]) - __uint_as_float(ei[j]));
+                                xi[j] = __float_as_uint(__uint_as_float(xi[j]) + __uint_as_float(er[j]));
+                            }
+                        } else {
+                            tmem_ld16(taddr + c0, xr);
+                            tmem_ld16(taddr + NT + c0, xi);
+                            tmem_ld_wait();
+                        }
+#pragma unroll
+                        for (int j4 = 0; j4 < 16; j4 += 4) {
+                            const int4 ct = *reinterpret_cast<const int4*>(coltab + c0 + j4);
+                            const int32_t cd[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = j4 + jj;
+                                float2 v = make_float2(__uint_as_float(xr[j]), __uint_as_float(xi[j]));
+                                if (!unit_alpha) v = make_float2(ar * v.x - ai * v.y, ar * v.y + ai * v.x);
+                                float2* dst = rbase + cd[jj];
+                                if (has_beta) {
+                                    const float2 old = *dst;
+                                    v.x += br * old.x - bi * old.y;
+                                    v.y += br * old.y + bi * old.x;
+                                }
+                                *dst = v;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accempty_bar(set));
+            }
+        } else
         for (int64_t t = t0; t < ntiles; t += tstep, i += (uint32_t)G) {
             const uint32_t set = i % NSETS;
             const int64_t hi_cur = hi_next;
@@ -1292,6 +1361,8 @@ int launch_stem_tc(tnb_ctx* ctx, StemTcArgs a) {
     // two epilogue groups whenever the form has two TMEM sets and the second staging tile leaves >= 6 raw stages
     // (TNB_STEM_EGROUPS=1: one group, comparison)
     static const int eg_env = [] { const char* e = getenv("TNB_STEM_EGROUPS"); return e ? atoi(e) : 2; }();
+    static const int direct_env = [] { const char* e = getenv("TNB_STEM_DIRECT"); return e ? atoi(e) : 1; }();   // 0: always staged (comparison / tests)
+    if (!direct_env || NT > 64 || a.K > 128) a.direct = 0;
     a.egroups = (NT <= 64 && !WIDE64 && eg_env == 2) ? 2 : 1;
     if (a.egroups == 2 && sk_layout(NT, a) < 6) a.egroups = 1;
     if (sk_layout(NT, a) < 3) return -1;
@@ -1406,6 +1477,7 @@ int tnb_launch_c64_stem_tc(tnb_ctx* ctx, const StemArgs& e, void* ws, int npass)
     a.run_shift = 0;
     while ((1 << (a.run_shift + 1)) <= e.run) a.run_shift++;
     a.additive = e.additive;
+    a.direct = e.direct;
     a.vec2 = (e.run >= 2 && e.even && ((uintptr_t)e.C % 16) == 0) ? 1 : 0;
     a.alpha[0] = (float)e.alpha[0]; a.alpha[1] = (float)e.alpha[1];
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];

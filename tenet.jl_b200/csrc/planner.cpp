@@ -234,8 +234,12 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         // class 1: SIMT streaming (N*K small: FP32 FMA keeps up with HBM); class 2: tensor-core stem (c64 only)
         // the tensor-core stem kernel takes <= 64 small-side columns per pass; wider small operands (<= 256) run as
         // several passes that re-read the big operand (still far fewer bytes than a tile kernel without overlap)
-        // K > 128 in the 128-column form (TMEM chunks of 128 k added in the staging tile): TNB_STEM_KMAX=512 (experiment)
-        static const int64_t kmax_wide = [] { const char* e = getenv("TNB_STEM_KMAX"); return e ? atoll(e) : 128ll; }();
+        // K > 128 in the 128-column form (chunks of 128 k summed round-to-nearest): taken when the small operand is exactly
+        // one pass wide (K <= 512) — the tile GEMM would write such an output 128 columns at a time, uncoalesced for every
+        // layout but column-fastest (sycamore53_m14's 128 x 524288 x 512 step: 1.69 -> 1.12 ms).  With several passes the
+        // tile GEMM re-reads less and wins; TNB_STEM_KMAX=512 sends those here as well (experiment, measured slower).
+        static const int64_t kmax_env = [] { const char* e = getenv("TNB_STEM_KMAX"); return e ? atoll(e) : 128ll; }();
+        const int64_t kmax_wide = Ns == 128 ? std::max<int64_t>(kmax_env, 512) : kmax_env;
         if (wide && (Ns % 128 != 0 || S.K < 64 || S.K > kmax_wide)) continue;
         const int64_t nper = wide ? 128 : (Ns > 64 ? 64 : Ns);
         const int64_t npass = Ns / std::max<int64_t>(nper, 1);
@@ -314,10 +318,42 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         S.st_additive = additive; S.st_even = even;
         S.st_rel_small = true;
         for (int64_t v : S.st_rel) if (v < 0 || v >= ((int64_t)1 << 31)) { S.st_rel_small = false; break; }
-        if (getenv("TNB_DEBUG_STEM"))
-            fprintf(stderr, "[stem] M=%lld N=%lld K=%lld big=%lld small=%lld tc=%d swap=%d TM=%lld ncol=%lld passes=%lld run=%lld additive=%d even=%d contig=%d\n",
+        // Direct epilogue of the tensor-core stem kernel (<= 64 columns per pass): an epilogue thread owns one row of the tile
+        // and a warp stores one column of 32 consecutive rows per instruction.  That is as good as the staged, sorted
+        // write-out whenever those 32 addresses are whole 64-byte pieces (8 complex64, <= 4 lines per instruction): the big
+        // side's fastest rows are the output's fastest index — then the shared-memory round trip of the staging tile is
+        // skipped altogether.  TNB_STEM_DIRECT=0 (read at plan time: test hook) keeps every step on the staged path;
+        // TNB_STEM_NO_ADDITIVE (the test hook of the general rank table) implies it.
+        S.st_direct = false;
+        {
+            const char* e = getenv("TNB_STEM_DIRECT");
+            bool ok = !simt && ncol <= 64 && S.K <= 128 && S.st_rel_small && TM % 32 == 0 && !(e && atoi(e) == 0) &&
+                      getenv("TNB_STEM_NO_ADDITIVE") == nullptr;
+            for (int64_t v : cb.hi) if (v & 7) { ok = false; break; }
+            for (int64_t ps = 0; ps < passes && ok; ps++) {
+                const int64_t* rel = S.st_rel.data() + ps * cnt;
+                const int64_t* pos = S.st_pos.data() + ps * cnt;
+                for (int64_t n = 0; n < ncol && ok; n++) if ((rel[pos[n]] - rel[pos[0]]) & 7) ok = false;
+                for (int64_t q = 0; q < TM / 32 && ok; q++) {
+                    std::vector<int64_t> piece;
+                    for (int64_t l = 0; l < 32; l++) piece.push_back(rel[pos[(q * 32 + l) * ncol]] >> 3);
+                    std::sort(piece.begin(), piece.end());
+                    for (size_t i = 0; i < piece.size() && ok; i += 8)
+                        if (piece[i] != piece[i + 7] || (i + 8 < piece.size() && piece[i + 8] == piece[i])) ok = false;
+                }
+            }
+            S.st_direct = ok;
+        }
+        if (getenv("TNB_DEBUG_STEM")) {
+            // which bits of the in-tile rank belong to the big-side rows / the small-side columns (pass 0)
+            int64_t rowbits = 0, colbits = 0;
+            for (int64_t ml = 0; ml < TM; ml++) rowbits |= S.st_pos[(size_t)(ml * ncol)] - S.st_pos[0];
+            for (int64_t n = 0; n < ncol; n++) colbits |= S.st_pos[(size_t)n] - S.st_pos[0];
+            fprintf(stderr, "[stem] M=%lld N=%lld K=%lld big=%lld small=%lld tc=%d swap=%d TM=%lld ncol=%lld passes=%lld run=%lld additive=%d even=%d contig=%d direct=%d rowbits=0x%llx colbits=0x%llx\n",
                     (long long)S.M, (long long)S.N, (long long)S.K, (long long)Mb, (long long)Ns, (int)!simt, sw, (long long)TM,
-                    (long long)ncol, (long long)passes, (long long)R, (int)additive, (int)even, (int)contig);
+                    (long long)ncol, (long long)passes, (long long)R, (int)additive, (int)even, (int)contig, (int)S.st_direct,
+                    (unsigned long long)rowbits, (unsigned long long)colbits);
+        }
         S.st_npass = (int32_t)passes; S.st_ncol = (int32_t)ncol;
         S.st_hi = cb.hi;
         S.st_ok = true; S.st_swap = sw != 0; S.st_tm = (int32_t)TM; S.st_contig = contig;

@@ -281,6 +281,46 @@ def test_wide_stem_on_cta_pairs_bit_identical(ctx, N, K):
     assert np.abs(c0.parent - r).max() / np.abs(r).max() < C64_STEP_BOUND
 
 
+@pytest.mark.parametrize("N,K", [(16, 32), (32, 32), (32, 128), (64, 16), (64, 64), (48, 24)])
+def test_stem_tc_direct_epilogue_bit_identical(ctx, monkeypatch, N, K):
+    """<= 64-column stem passes store rows straight from registers when a warp's 32 rows of one column are whole 64-byte
+    pieces in the output (planner: st_direct); TNB_STEM_DIRECT=0 at plan time keeps the staged, sorted write-out.  Same
+    MMAs, same order: bit-identical, for layouts on both sides of the criterion, with conj and beta = 1 accumulation."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(N * 7 + K)
+    a = crand(rng, (2,) * 17 + (K,))
+    b = crand(rng, (N, K))
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"]).conj()
+    ref = np.tensordot(a.astype(np.complex128), np.conj(b).astype(np.complex128), axes=([17], [1]))
+    # m-fastest (direct), 8 rows then n (direct, 4 pieces per store), 4 rows then n (staged), n fastest (staged)
+    for out in [None, big[:3] + ["n"] + big[3:], big[:5] + ["n"] + big[5:], big[:2] + ["n"] + big[2:], ["n"] + big]:
+        res = {}
+        for direct in ("1", "0"):
+            monkeypatch.setenv("TNB_STEM_DIRECT", direct)
+            res[direct] = tb.binary_einsum(ta, tb_, out=out).parent.copy()
+            assert ctx.last_kernel == "stem_tc", ctx.last_kernel
+        monkeypatch.delenv("TNB_STEM_DIRECT")
+        r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        assert np.abs(res["1"] - r).max() / np.abs(r).max() < C64_STEP_BOUND
+        assert np.array_equal(res["0"], res["1"]), f"out={out}: max diff {np.abs(res['0'] - res['1']).max():.3e}"
+    # beta = 1 (slice accumulation into the output): executing the one-step plan twice doubles every element exactly
+    tn = tb.TensorNetwork([ta, tb_])
+    for out in [big + ["n"], big[:3] + ["n"] + big[3:]]:
+        path = tb.einexpr(tn, output=out)
+        plan = tb.ContractionPlan(tn, path, output=out, ctx=ctx)
+        assert plan.step_info(0)["kernel_name"] == "stem_tc"
+        plan.zero_output()
+        plan.execute(accumulate=True)
+        once = plan.result().parent.copy()
+        plan.execute(accumulate=True)
+        twice = plan.result().parent.copy()
+        plan.close()
+        r = np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        assert np.abs(once - r).max() / np.abs(r).max() < C64_STEP_BOUND
+        assert np.array_equal(twice, once + once)
+
+
 def test_stem_tc_rank_table_path(ctx, monkeypatch):
     """the general (non-separable rank) epilogue of the stem kernel: forced through TNB_STEM_NO_ADDITIVE."""
     import tenet_jl_b200 as tb
@@ -300,11 +340,11 @@ def test_stem_tc_rank_table_path(ctx, monkeypatch):
         assert err < C64_STEP_BOUND, err
 
 
-@pytest.mark.parametrize("N,K", [(128, 256), (256, 512), (128, 200)])
+@pytest.mark.parametrize("N,K", [(128, 256), (128, 512), (256, 512), (128, 200)])
 def test_stem_tc_long_k(ctx, N, K):
-    """huge x small with K > 128: the tile GEMM kernel by default; with TNB_STEM_KMAX=512 in the environment the
-    128-column stem passes take K <= 512 in TMEM chunks of 128 k that are added in the staging tile.  Both accumulate
-    chunks round-to-nearest, so the bound is the same."""
+    """huge x small with K > 128: a small operand of exactly 128 columns goes through the 128-column stem pass
+    (K <= 512, chunks of 128 k summed round-to-nearest); wider ones take the tile GEMM kernel unless TNB_STEM_KMAX=512
+    is in the environment.  Both accumulate chunks round-to-nearest, so the bound is the same."""
     import os
     import tenet_jl_b200 as tb
     rng = np.random.default_rng(N + K)
@@ -315,6 +355,8 @@ def test_stem_tc_long_k(ctx, N, K):
     hi = np.complex128
     ref = np.tensordot(a.astype(hi), b.astype(hi), axes=([17], [1]))
     kmax = int(os.environ.get("TNB_STEM_KMAX", "128"))
+    if N == 128:
+        kmax = max(kmax, 512)
     for out in [None, big[:2] + ["n"] + big[2:], ["n"] + big[8:] + big[:8]]:
         c = tb.binary_einsum(ta, tb_, out=out)
         assert ctx.last_kernel == ("stem_tc" if K <= kmax and K % 8 == 0 else "c64_tf32x3"), ctx.last_kernel
