@@ -183,6 +183,7 @@ struct TcArgs {
     const int64_t* st_rel;
     const int64_t* st_pos;
     int32_t st_run_shift, st_vec2, st_rel_small;   // log2 run length; 16-byte pairs allowed; every rel entry fits int32
+    int32_t st_direct;        // rows stored straight from the drain registers (planner.cpp st_direct): no staging tile
 };
 
 __device__ __forceinline__ int64_t tabc(const TabRef& t, uint32_t i) {
@@ -1432,7 +1433,7 @@ int tnb_launch_c64_tc(tnb_ctx* ctx, const EinsumArgs& e, int nt, int64_t lda, in
     a.beta[0] = (float)e.beta[0]; a.beta[1] = (float)e.beta[1];
     a.ws = (float2*)e.ws;
     a.st_hi = a.st_rel = a.st_pos = nullptr;
-    a.st_run_shift = a.st_vec2 = a.st_rel_small = 0;
+    a.st_run_shift = a.st_vec2 = a.st_rel_small = a.st_direct = 0;
     a.splitk = e.splitk > 1 ? (uint32_t)e.splitk : 1u;
     a.kb_per_split = e.splitk > 1 ? (uint32_t)e.kchunk : (uint32_t)((e.K + TC_BK - 1) / TC_BK);
     if (!chunked && a.splitk == 1 && nt >= 128) {
@@ -1525,6 +1526,7 @@ int tnb_launch_c64_pair_staged(tnb_ctx* ctx, const StemArgs& e, int64_t Nsmall, 
     while ((1 << (a.st_run_shift + 1)) <= e.run) a.st_run_shift++;
     a.st_vec2 = (e.run >= 2 && e.even && ((uintptr_t)e.C % 16) == 0) ? 1 : 0;
     a.st_rel_small = rel_small ? 1 : 0;
+    a.st_direct = (e.direct && rel_small) ? 1 : 0;
     if (!tc_acc_ok(a)) return -1;
     return launch_tc_pair<true>(ctx, a);
 }

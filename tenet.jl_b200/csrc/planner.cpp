@@ -318,7 +318,8 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         S.st_additive = additive; S.st_even = even;
         S.st_rel_small = true;
         for (int64_t v : S.st_rel) if (v < 0 || v >= ((int64_t)1 << 31)) { S.st_rel_small = false; break; }
-        // Direct epilogue of the tensor-core stem kernel (<= 64 columns per pass): an epilogue thread owns one row of the tile
+        // Direct epilogue of the tensor-core stem kernels (1-CTA kernel: <= 64 columns per pass; CTA-pair kernel: 128-column
+        // passes): an epilogue thread owns one row of the tile
         // and a warp stores one column of 32 consecutive rows per instruction.  That is as good as the staged, sorted
         // write-out whenever those 32 addresses are whole 64-byte pieces (8 complex64, <= 4 lines per instruction): the big
         // side's fastest rows are the output's fastest index — then the shared-memory round trip of the staging tile is
@@ -327,7 +328,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         S.st_direct = false;
         {
             const char* e = getenv("TNB_STEM_DIRECT");
-            bool ok = !simt && ncol <= 64 && S.K <= 128 && S.st_rel_small && TM % 32 == 0 && !(e && atoi(e) == 0) &&
+            bool ok = !simt && S.st_rel_small && TM % 32 == 0 && !(e && atoi(e) == 0) &&
                       getenv("TNB_STEM_NO_ADDITIVE") == nullptr;
             for (int64_t v : cb.hi) if (v & 7) { ok = false; break; }
             for (int64_t ps = 0; ps < passes && ok; ps++) {

@@ -281,11 +281,12 @@ def test_wide_stem_on_cta_pairs_bit_identical(ctx, N, K):
     assert np.abs(c0.parent - r).max() / np.abs(r).max() < C64_STEP_BOUND
 
 
-@pytest.mark.parametrize("N,K", [(16, 32), (32, 32), (32, 128), (64, 16), (64, 64), (48, 24)])
+@pytest.mark.parametrize("N,K", [(16, 32), (32, 32), (32, 128), (64, 16), (64, 64), (48, 24), (128, 64), (256, 128), (128, 256)])
 def test_stem_tc_direct_epilogue_bit_identical(ctx, monkeypatch, N, K):
-    """<= 64-column stem passes store rows straight from registers when a warp's 32 rows of one column are whole 64-byte
-    pieces in the output (planner: st_direct); TNB_STEM_DIRECT=0 at plan time keeps the staged, sorted write-out.  Same
-    MMAs, same order: bit-identical, for layouts on both sides of the criterion, with conj and beta = 1 accumulation."""
+    """Stem passes (1-CTA kernel: <= 64 columns, CTA-pair kernel: 128 columns) store rows straight from registers when a
+    warp's 32 rows of one column are whole 64-byte pieces in the output (planner: st_direct); TNB_STEM_DIRECT=0 at plan
+    time keeps the staged, sorted write-out.  Same MMAs, same order: bit-identical, for layouts on both sides of the
+    criterion, with conj and beta = 1 accumulation."""
     import tenet_jl_b200 as tb
     rng = np.random.default_rng(N * 7 + K)
     a = crand(rng, (2,) * 17 + (K,))
