@@ -295,7 +295,9 @@ def test_stem_tc_direct_epilogue_bit_identical(ctx, monkeypatch, N, K):
     ta, tb_ = tb.Tensor(a, big + ["k"]), tb.Tensor(b, ["n", "k"]).conj()
     ref = np.tensordot(a.astype(np.complex128), np.conj(b).astype(np.complex128), axes=([17], [1]))
     # m-fastest (direct), 8 rows then n (direct, 4 pieces per store), 4 rows then n (staged), n fastest (staged)
-    for out in [None, big[:3] + ["n"] + big[3:], big[:5] + ["n"] + big[5:], big[:2] + ["n"] + big[2:], ["n"] + big]:
+    # ... and the fastest row as the output's slowest index (direct: two 128-byte pieces per store, tile bases far apart)
+    for out in [None, big[:3] + ["n"] + big[3:], big[:5] + ["n"] + big[5:], big[:2] + ["n"] + big[2:], ["n"] + big,
+                big[1:] + ["n"] + big[:1]]:
         res = {}
         for direct in ("1", "0"):
             monkeypatch.setenv("TNB_STEM_DIRECT", direct)
