@@ -146,7 +146,7 @@ int run_step(tnb_ctx* ctx, int dtype, const StepSpec& S, const int64_t* dev_blob
         t.M = sw ? S.N : S.M; t.N = (int32_t)(sw ? S.M : S.N); t.K = (int32_t)S.K;
         t.lda = S.K > 1 ? (sw ? S.bk.stride : S.ak.stride) : t.M;
         t.TM = S.st_tm; t.contig = S.st_contig ? 1 : 0; t.run = S.st_run;
-        t.additive = S.st_additive ? 1 : 0; t.even = S.st_even ? 1 : 0; t.direct = S.st_direct ? 1 : 0;
+        t.additive = S.st_additive ? 1 : 0; t.even = S.st_even ? 1 : 0; t.direct = S.st_direct ? 1 : 0; t.pairs = S.st_pairs ? 1 : 0;
         t.conjA = sw ? S.conjB : S.conjA; t.conjB = sw ? S.conjA : S.conjB;
         t.bn = sw ? a.am : a.bn; t.bk = sw ? a.ak : a.bk;
         t.hi = dev_blob + S.st_hi_pos; t.rel = dev_blob + S.st_rel_pos; t.pos = dev_blob + S.st_pos_pos;

@@ -17,6 +17,7 @@
 //     addresses whatever the consumer's layout is.
 // Persistent grid (a few CTAs per SM, tiles strided over CTAs).  Algorithmic bytes per launch: sizeof(T)*(M*K + M*N).
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 #include "tnb_internal.h"
 
@@ -137,6 +138,129 @@ __global__ void __launch_bounds__(ST_THREADS, (sizeof(E) / 4 * VM * NMAX <= 16) 
     }
 }
 
+// Direct form (planner: st_direct — a warp's 32 consecutive rows of one column are whole 64-byte pieces of the output):
+// no staging tile, no rank tables, no barrier after the set-up.  A thread loads its VM rows of A (K independent 16-byte
+// loads), multiplies with the broadcast small operand and stores its N results straight to C at
+// hi[tile] + rowaddr[ml] + coldelta[n]; every warp free-runs over its tiles, so loads, FMAs and stores of different warps
+// overlap instead of alternating CTA-wide between a load phase and a write-out phase (ncu r2 on the complex128
+// 1024^2 x 6 x 6 step of configs[4]: the staged form was latency-bound at 0.35 - 0.43 of HBM, 54 % of the stalls on the
+// consumers of the global loads, 9 % on the two barriers per tile).  PAIR (VM = 2 only): rows 2i, 2i+1 are adjacent in the
+// output, both results of a column go out as one 16-byte store.
+template <typename E, int VM, int NMAX, bool PAIR>
+__global__ void __launch_bounds__(ST_THREADS, (sizeof(E) / 4 * VM * NMAX <= 16) ? 4 : ((sizeof(E) / 4 * VM * NMAX <= 32) ? 3 : 2)) stem_direct_kernel(const StemArgs p) {
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int N = p.N, K = p.K, TM = p.TM;
+    E* Bs = reinterpret_cast<E*>(st_smem);                                   // [K][N]
+    int32_t* coldelta = reinterpret_cast<int32_t*>(Bs + ((K * N + 1) & ~1)); // [NMAX]
+    int32_t* rowaddr = coldelta + NMAX;                                      // [TM]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < K * N; i += (int)blockDim.x) {
+        const int n = i % N, k = i / N;
+        E v = reinterpret_cast<const E*>(p.B)[stab(p.bn, n) + stab(p.bk, k)];
+        if (p.conjB) v.y = -v.y;
+        Bs[k * N + n] = v;
+    }
+    {
+        const int64_t a0 = p.rel[p.pos[0]];
+        for (int i = tid; i < NMAX; i += (int)blockDim.x) coldelta[i] = i < N ? (int32_t)(p.rel[p.pos[i]] - a0) : 0;
+        for (int i = tid; i < TM; i += (int)blockDim.x) rowaddr[i] = (int32_t)p.rel[p.pos[(int64_t)i * N]];
+    }
+    __syncthreads();
+
+    const E* __restrict__ A = reinterpret_cast<const E*>(p.A);
+    E* __restrict__ C = reinterpret_cast<E*>(p.C);
+    const bool has_beta = (p.beta[0] != 0.0) || (p.beta[1] != 0.0);
+    const bool unit_alpha = p.alpha[0] == 1.0 && p.alpha[1] == 0.0;
+    const int64_t ntiles = p.M / TM;
+    struct __align__(16) Vec { E v[VM]; };
+
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t m0 = t * TM;
+        E* base = C + p.hi[t];
+        for (int ml = tid * VM; ml < TM; ml += (int)blockDim.x * VM) {
+            E acc[VM][NMAX];
+#pragma unroll
+            for (int v = 0; v < VM; v++)
+#pragma unroll
+                for (int n = 0; n < NMAX; n++) acc[v][n] = czero((E*)0);
+            const E* src = A + m0 + ml;
+            if (K <= 8) {
+                // all K loads of the row in flight before the first FMA (the kernel is latency-bound: bytes in flight per
+                // SM = resident warps x 32 x K x 16 B)
+                Vec ar[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < K) ar[k] = *reinterpret_cast<const Vec*>(src + (int64_t)k * p.lda);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k < K) {
+                        if (p.conjA) {
+#pragma unroll
+                            for (int v = 0; v < VM; v++) ar[k].v[v].y = -ar[k].v[v].y;
+                        }
+                        const E* brow = Bs + k * N;
+#pragma unroll
+                        for (int n = 0; n < NMAX; n++) {
+                            if (n < N) {
+                                const E b = brow[n];
+#pragma unroll
+                                for (int v = 0; v < VM; v++) cmac(acc[v][n], ar[k].v[v], b);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < K; k++) {
+                    Vec a = *reinterpret_cast<const Vec*>(src + (int64_t)k * p.lda);
+                    if (p.conjA) {
+#pragma unroll
+                        for (int v = 0; v < VM; v++) a.v[v].y = -a.v[v].y;
+                    }
+                    const E* brow = Bs + k * N;
+#pragma unroll
+                    for (int n = 0; n < NMAX; n++) {
+                        if (n < N) {
+                            const E b = brow[n];
+#pragma unroll
+                            for (int v = 0; v < VM; v++) cmac(acc[v][n], a.v[v], b);
+                        }
+                    }
+                }
+            }
+            int32_t ra[VM];
+#pragma unroll
+            for (int v = 0; v < VM; v++) ra[v] = rowaddr[ml + v];
+#pragma unroll
+            for (int n = 0; n < NMAX; n++) {
+                if (n < N) {
+                    const int32_t cd = coldelta[n];
+                    if (PAIR) {
+                        Vec* dst = reinterpret_cast<Vec*>(base + ra[0] + cd);
+                        Vec o;
+#pragma unroll
+                        for (int v = 0; v < VM; v++) o.v[v] = unit_alpha ? acc[v][n] : cscale(p.alpha, acc[v][n]);
+                        if (has_beta) {
+                            const Vec old = *dst;
+#pragma unroll
+                            for (int v = 0; v < VM; v++) { const E q = cscale(p.beta, old.v[v]); o.v[v].x += q.x; o.v[v].y += q.y; }
+                        }
+                        *dst = o;
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VM; v++) {
+                            E* dst = base + ra[v] + cd;
+                            E o = unit_alpha ? acc[v][n] : cscale(p.alpha, acc[v][n]);
+                            if (has_beta) { const E q = cscale(p.beta, *dst); o.x += q.x; o.y += q.y; }
+                            *dst = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <typename E, int VM>
 int launch(tnb_ctx* ctx, const StemArgs& a) {
     const size_t esz = sizeof(E);
@@ -169,6 +293,40 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
         if (grid < 1) return TNB_OK;                                                                               \
         stem_kernel<E, VM, NMAX><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);                            \
     } while (0)
+    // direct form: the set-up tables replace the staging tile (TNB_STEM_DIRECT is honoured at plan time; C must be 16-byte
+    // aligned for the paired stores)
+#define ST_LAUNCH_DIRECT(NMAX, PAIR_)                                                                              \
+    do {                                                                                                           \
+        const size_t dsmem = (((size_t)a.K * a.N + 1) & ~(size_t)1) * esz + ((size_t)NMAX + (size_t)a.TM) * 4;     \
+        if (dsmem > 48 * 1024)                                                                                     \
+            TNB_CUDA_CHECK(ctx, cudaFuncSetAttribute(stem_direct_kernel<E, VM, NMAX, PAIR_>,                       \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));   \
+        int resident = 0;                                                                                          \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, stem_direct_kernel<E, VM, NMAX, PAIR_>,       \
+                                                          threads, dsmem) != cudaSuccess || resident < 1)          \
+            resident = 1;                                                                                          \
+        int64_t grid = (int64_t)ctx->sm_count * resident;                                                          \
+        if (grid > ntiles) grid = ntiles;                                                                          \
+        if (grid < 1) return TNB_OK;                                                                               \
+        stem_direct_kernel<E, VM, NMAX, PAIR_><<<(unsigned)grid, threads, dsmem, ctx->stream>>>(a);             \
+    } while (0)
+    static const int simt_direct = [] { const char* e = getenv("TNB_STEM_SIMT_DIRECT"); return e ? atoi(e) : 1; }();   // 0: staged form only (comparison)
+    if (a.direct && simt_direct) {
+        const bool pair = VM == 2 && a.pairs && ((uintptr_t)a.C % 16) == 0;
+        if (pair) {
+            if (a.N <= 4) ST_LAUNCH_DIRECT(4, (VM == 2));
+            else if (a.N <= 8) ST_LAUNCH_DIRECT(8, (VM == 2));
+            else ST_LAUNCH_DIRECT(16, (VM == 2));
+        } else {
+            if (a.N <= 4) ST_LAUNCH_DIRECT(4, false);
+            else if (a.N <= 8) ST_LAUNCH_DIRECT(8, false);
+            else ST_LAUNCH_DIRECT(16, false);
+        }
+        ctx->launches++;
+        TNB_CUDA_CHECK(ctx, cudaGetLastError());
+        return TNB_OK;
+    }
+#undef ST_LAUNCH_DIRECT
     if (a.N <= 4) ST_LAUNCH(4);
     else if (a.N <= 8) ST_LAUNCH(8);
     else ST_LAUNCH(16);

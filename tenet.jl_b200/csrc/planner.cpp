@@ -318,32 +318,50 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         S.st_additive = additive; S.st_even = even;
         S.st_rel_small = true;
         for (int64_t v : S.st_rel) if (v < 0 || v >= ((int64_t)1 << 31)) { S.st_rel_small = false; break; }
-        // Direct epilogue of the tensor-core stem kernels (1-CTA kernel: <= 64 columns per pass; CTA-pair kernel: 128-column
-        // passes): an epilogue thread owns one row of the tile
-        // and a warp stores one column of 32 consecutive rows per instruction.  That is as good as the staged, sorted
-        // write-out whenever those 32 addresses are whole 64-byte pieces (8 complex64, <= 4 lines per instruction): the big
-        // side's fastest rows are the output's fastest index — then the shared-memory round trip of the staging tile is
-        // skipped altogether.  TNB_STEM_DIRECT=0 (read at plan time: test hook) keeps every step on the staged path;
-        // TNB_STEM_NO_ADDITIVE (the test hook of the general rank table) implies it.
-        S.st_direct = false;
+        // Direct epilogue of the stem kernels (tensor-core forms: <= 64 columns per pass on the 1-CTA kernel, 128-column passes
+        // on the CTA-pair kernel; SIMT form: N <= 16): a thread owns one row of the tile and a warp stores one column of 32
+        // consecutive rows per instruction.  That is as good as the staged, sorted write-out whenever those 32 addresses are
+        // whole 32-byte sectors (4 complex64 / 2 complex128) in <= 4 lines per instruction: the big side's fastest rows are
+        // the output's fastest index — then the shared-memory round trip of the staging tile is skipped altogether.
+        // TNB_STEM_DIRECT (read at plan time: test hook): 0 keeps every step on the staged path, 1 asks for whole 64-byte
+        // pieces (the first version; 128 x 8388608 x 128 of the committed path gains 3 % from the 32-byte rule: its rows
+        // fill sectors 0-1 / 2-3 of a line in alternate columns); TNB_STEM_NO_ADDITIVE (the test hook of the general rank
+        // table) implies 0.  st_pairs: rows 2i, 2i+1 are adjacent in the output (the SIMT complex64 form stores 16 bytes).
+        S.st_direct = false; S.st_pairs = false;
         {
             const char* e = getenv("TNB_STEM_DIRECT");
-            bool ok = !simt && S.st_rel_small && TM % 32 == 0 && !(e && atoi(e) == 0) &&
-                      getenv("TNB_STEM_NO_ADDITIVE") == nullptr;
-            for (int64_t v : cb.hi) if (v & 7) { ok = false; break; }
+            const int mode = e ? atoi(e) : 2;
+            const int64_t pe = (mode == 1 ? 64 : 32) / (int64_t)elem_size;       // elements per piece
+            bool ok = S.st_rel_small && TM % 32 == 0 && mode != 0 && pe >= 1 && getenv("TNB_STEM_NO_ADDITIVE") == nullptr;
+            bool pairs = TM % 2 == 0;
+            const int64_t line = 128 / (int64_t)elem_size;
+            for (int64_t v : cb.hi) { if (v % pe) ok = false; if (v & 1) pairs = false; }
             for (int64_t ps = 0; ps < passes && ok; ps++) {
                 const int64_t* rel = S.st_rel.data() + ps * cnt;
                 const int64_t* pos = S.st_pos.data() + ps * cnt;
-                for (int64_t n = 0; n < ncol && ok; n++) if ((rel[pos[n]] - rel[pos[0]]) & 7) ok = false;
+                for (int64_t n = 0; n < ncol && ok; n++) {
+                    if ((rel[pos[n]] - rel[pos[0]]) % pe) ok = false;
+                    if ((rel[pos[n]] - rel[pos[0]]) & 1) pairs = false;
+                }
                 for (int64_t q = 0; q < TM / 32 && ok; q++) {
                     std::vector<int64_t> piece;
-                    for (int64_t l = 0; l < 32; l++) piece.push_back(rel[pos[(q * 32 + l) * ncol]] >> 3);
+                    std::set<int64_t> lines;
+                    for (int64_t l = 0; l < 32; l++) {
+                        const int64_t a = rel[pos[(q * 32 + l) * ncol]];
+                        piece.push_back(a / pe);
+                        lines.insert(a / line);
+                    }
                     std::sort(piece.begin(), piece.end());
-                    for (size_t i = 0; i < piece.size() && ok; i += 8)
-                        if (piece[i] != piece[i + 7] || (i + 8 < piece.size() && piece[i + 8] == piece[i])) ok = false;
+                    for (size_t i = 0; i < piece.size() && ok; i += (size_t)pe)
+                        if (piece[i] != piece[i + (size_t)pe - 1] || (i + (size_t)pe < piece.size() && piece[i + (size_t)pe] == piece[i])) ok = false;
+                    if (lines.size() > 4) ok = false;
+                }
+                for (int64_t ml = 0; ml + 1 < TM && pairs; ml += 2) {
+                    const int64_t a0 = rel[pos[ml * ncol]], a1 = rel[pos[(ml + 1) * ncol]];
+                    if (a1 != a0 + 1 || (a0 & 1)) pairs = false;
                 }
             }
-            S.st_direct = ok;
+            S.st_direct = ok; S.st_pairs = ok && pairs;
         }
         if (getenv("TNB_DEBUG_STEM")) {
             // which bits of the in-tile rank belong to the big-side rows / the small-side columns (pass 0)

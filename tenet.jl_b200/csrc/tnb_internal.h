@@ -75,7 +75,8 @@ struct StepSpec {
     bool st_ok = false, st_swap = false, st_contig = false, st_tc = false;
     int32_t st_npass = 1, st_ncol = 0;   // passes over the small operand's columns, columns per pass
     bool st_additive = false, st_even = false;   // see StemArgs
-    bool st_direct = false;                      // tensor-core stem kernel may store rows straight from registers (planner.cpp)
+    bool st_direct = false;                      // stem kernels may store rows straight from registers (planner.cpp)
+    bool st_pairs = false;                       // ... and rows 2i, 2i+1 are adjacent in the output (16-byte stores of two complex64)
     bool st_rel_small = false;                   // every entry of st_rel fits an int32 (run bases kept in shared memory)
     int32_t st_tm = 0, st_run = 1;   // tile rows; length of the contiguous output runs inside a tile (power of two)
     std::vector<int64_t> st_hi, st_rel, st_pos;
@@ -167,7 +168,8 @@ struct StemArgs {
     int32_t run;              // contiguous run length of the sorted pattern (power of two): rel[j] = rel[j & ~(run-1)] + (j & (run-1))
     int32_t additive;         // pos[ml*N + n] == pos[ml*N] | (pos[n] - pos[0]), disjoint bits (rank separable in row and column)
     int32_t even;             // every tile base (hi) and every run base (rel[j*run]) is even: 16-byte aligned pairs
-    int32_t direct;           // a warp's 32 rows of one column fill whole 32-byte sectors: no staging tile needed (stem_tc only)
+    int32_t direct;           // a warp's 32 rows of one column are whole 64-byte pieces of the output: no staging tile needed
+    int32_t pairs;            // direct && rows 2i, 2i+1 adjacent in the output (SIMT complex64 form: 16-byte stores)
     TabRef bn, bk;
     const int64_t* hi;        // [M/TM] tile base offsets in C
     const int64_t* rel;       // [TM*N] ascending offsets inside a tile

@@ -238,7 +238,8 @@ def test_stem_plan_flags(built_lib):
 
 def test_stem_direct_epilogue_criterion(built_lib, monkeypatch, capfd):
     """planner.cpp st_direct: a stem step may store rows straight from registers exactly when a warp's 32 consecutive rows
-    of one column are whole 64-byte pieces (8 complex64) of the output.  Read from the planner trace (TNB_DEBUG_STEM)."""
+    of one column are whole 32-byte sectors (4 complex64) of the output in at most 4 lines.  Read from the planner trace
+    (TNB_DEBUG_STEM)."""
     import re
     import tenet_jl_b200 as tb
     monkeypatch.setenv("TNB_DEBUG_STEM", "1")
@@ -264,8 +265,8 @@ def test_stem_direct_epilogue_criterion(built_lib, monkeypatch, capfd):
         assert direct_flag(N, K, big + ["n"]) == 1                       # rows fastest: 32 rows = 256 contiguous bytes
         assert direct_flag(N, K, big[:5] + ["n"] + big[5:]) == 1         # 32 rows, then the small index
         assert direct_flag(N, K, big[:3] + ["n"] + big[3:]) == 1         # 8 rows (64 bytes), then the small index
-        assert direct_flag(N, K, big[:2] + ["n"] + big[2:]) == 0         # 4 rows = 32-byte pieces: staged write-out
+        assert direct_flag(N, K, big[:2] + ["n"] + big[2:]) == 0         # 4 rows = 8 sectors in 8 lines per store: staged write-out
         assert direct_flag(N, K, ["n"] + big) == 0                       # small index fastest: staged write-out
         assert direct_flag(N, K, big[1:] + ["n"] + big[:1]) == 1         # lanes = m0..m4: two 128-byte pieces (m1..m4) per store
-        assert direct_flag(N, K, big[3:] + ["n"] + big[:3]) == 0         # only m3, m4 of the lane rows are adjacent: 32-byte pieces
+        assert direct_flag(N, K, big[3:] + ["n"] + big[:3]) == 0         # only m3, m4 of the lane rows are adjacent: 8 lines per store
         assert direct_flag(N, K, big + ["n"], env="0") == 0              # switch (read at plan time)

@@ -224,6 +224,47 @@ def test_stem_stream_kernel(ctx, dt, tol):
     assert np.abs(c.parent - r).max() / np.abs(r).max() < tol * 4
 
 
+@pytest.mark.parametrize("dt,tol", [(np.complex64, 2e-6), (np.complex128, 1e-13)])
+@pytest.mark.parametrize("N,K", [(4, 4), (6, 6), (8, 2), (16, 16)])
+def test_stem_direct_form_bit_identical(ctx, monkeypatch, dt, tol, N, K):
+    """SIMT stem kernel: rows stored straight from registers where the planner finds whole 64-byte pieces per warp store
+    (st_direct; 16-byte stores of two complex64 rows when they are adjacent), staged sorted write-out otherwise and under
+    TNB_STEM_DIRECT=0.  Same FMAs in the same order: bit-identical; non-power-of-two small operand (the 6 x 6 MPO step of
+    configs[4]), conj, beta = 1."""
+    import tenet_jl_b200 as tb
+    rng = np.random.default_rng(N * 11 + K)
+    a = crand(rng, (2,) * 17 + (K,), dt)
+    b = crand(rng, (N, K), dt)
+    big = [f"m{i}" for i in range(17)]
+    ta, tb_ = tb.Tensor(a, big + ["k"]).conj(), tb.Tensor(b, ["n", "k"])
+    ref = np.tensordot(np.conj(a).astype(np.complex128), b.astype(np.complex128), axes=([17], [1]))
+    outs = [None, big[:3] + ["n"] + big[3:], big[:5] + ["n"] + big[5:], big[1:] + ["n"] + big[:1],   # direct
+            big[:1] + ["n"] + big[1:], ["n"] + big]                                                   # staged
+    kern = "stem_tc" if (dt == np.complex64 and N % 16 == 0 and K % 8 == 0) else "stem"              # 16 x 16 complex64: tensor cores
+    for out in outs:
+        res = {}
+        for direct in ("1", "0"):
+            monkeypatch.setenv("TNB_STEM_DIRECT", direct)
+            res[direct] = tb.binary_einsum(ta, tb_, out=out).parent.copy()
+            assert ctx.last_kernel == kern, ctx.last_kernel
+        monkeypatch.delenv("TNB_STEM_DIRECT")
+        r = ref if out is None else np.transpose(ref, [(big + ["n"]).index(i) for i in out])
+        assert np.abs(res["1"] - r).max() / np.abs(r).max() < (tol if kern == "stem" else C64_STEP_BOUND)
+        assert np.array_equal(res["0"], res["1"]), f"out={out}: max diff {np.abs(res['0'] - res['1']).max():.3e}"
+    tn = tb.TensorNetwork([ta, tb_])
+    out = big + ["n"]
+    plan = tb.ContractionPlan(tn, tb.einexpr(tn, output=out), output=out, ctx=ctx)
+    assert plan.step_info(0)["kernel_name"] == kern
+    plan.zero_output()
+    plan.execute(accumulate=True)
+    once = plan.result().parent.copy()
+    plan.execute(accumulate=True)
+    twice = plan.result().parent.copy()
+    plan.close()
+    assert np.abs(once - ref).max() / np.abs(ref).max() < (tol if kern == "stem" else C64_STEP_BOUND)
+    assert np.array_equal(twice, once + once)
+
+
 @pytest.mark.parametrize("N,K", [(16, 16), (32, 128), (64, 64), (48, 8), (64, 16), (128, 64), (256, 16), (64, 128), (128, 128), (256, 96)])
 def test_stem_tc_kernel(ctx, N, K):
     """persistent tcgen05 stem kernel: huge x small, several consumer layouts, both orientations."""
