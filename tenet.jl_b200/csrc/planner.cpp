@@ -362,6 +362,10 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
                 }
             }
             S.st_direct = ok; S.st_pairs = ok && pairs;
+            if (getenv("TNB_DEBUG_STEM") && !ok)
+                fprintf(stderr, "[stem-direct] no: rel_small=%d TM=%lld pe=%lld hi0=%lld hi1=%lld col1=%lld row1=%lld row32=%lld\n", (int)S.st_rel_small, (long long)TM, (long long)pe,
+                        (long long)cb.hi[0], (long long)(cb.hi.size() > 1 ? cb.hi[1] : 0), (long long)(ncol > 1 ? S.st_rel[S.st_pos[1]] - S.st_rel[S.st_pos[0]] : 0),
+                        (long long)(S.st_rel[S.st_pos[ncol]] - S.st_rel[S.st_pos[0]]), (long long)(TM > 32 ? S.st_rel[S.st_pos[32 * ncol]] - S.st_rel[S.st_pos[0]] : 0));
         }
         if (getenv("TNB_DEBUG_STEM")) {
             // which bits of the in-tile rank belong to the big-side rows / the small-side columns (pass 0)

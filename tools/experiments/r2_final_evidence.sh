@@ -29,4 +29,7 @@ echo "bench rc=$?" >> gpurun_out/r2_bench_default.err
 cut -c1-300 gpurun_out/r2_bench_default.json; tail -3 gpurun_out/r2_bench_default.err
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
 cut -c1-300 gpurun_out/r2_bench_reference.json
+# (5) SIMT stem kernel: direct vs staged form on rows-fastest outputs (one process each)
+for v in 1 0 1 0; do TNB_STEM_SIMT_DIRECT=$v timeout 120 python tools/probes/simt_direct_probe.py 2>&1 | tail -1; done > gpurun_out/simt_direct_probe.txt
+cat gpurun_out/simt_direct_probe.txt | cut -c1-600
 du -sh gpurun_out
