@@ -331,7 +331,7 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
         {
             const char* e = getenv("TNB_STEM_DIRECT");
             const int mode = e ? atoi(e) : 2;
-            const int64_t pe = (mode == 1 ? 64 : 32) / (int64_t)elem_size;       // elements per piece
+            const int64_t pe = (mode == 1 ? 64 : 32) / (int64_t)elem_size;       // elements per piece (modes 2, 3: one sector)
             bool ok = S.st_rel_small && TM % 32 == 0 && mode != 0 && pe >= 1 && getenv("TNB_STEM_NO_ADDITIVE") == nullptr;
             bool pairs = TM % 2 == 0;
             const int64_t line = 128 / (int64_t)elem_size;
@@ -340,21 +340,27 @@ int tnb_build_step(const PlanTensor& A, const PlanTensor& B, const PlanTensor& C
                 const int64_t* rel = S.st_rel.data() + ps * cnt;
                 const int64_t* pos = S.st_pos.data() + ps * cnt;
                 for (int64_t n = 0; n < ncol && ok; n++) {
-                    if ((rel[pos[n]] - rel[pos[0]]) % pe) ok = false;
+                    if (!(simt && mode == 3) && (rel[pos[n]] - rel[pos[0]]) % pe) ok = false;
                     if ((rel[pos[n]] - rel[pos[0]]) & 1) pairs = false;
                 }
+                // mode 3 (experiment, SIMT form only): the rule is applied to ALL columns of the 32 rows together — a thread
+                // stores its N results back to back, so a small-operand index below the rows (the MPO bond of configs[4])
+                // still fills whole sectors within a few instructions of the same warp
+                const bool all_cols = simt && mode == 3;
                 for (int64_t q = 0; q < TM / 32 && ok; q++) {
                     std::vector<int64_t> piece;
                     std::set<int64_t> lines;
                     for (int64_t l = 0; l < 32; l++) {
-                        const int64_t a = rel[pos[(q * 32 + l) * ncol]];
-                        piece.push_back(a / pe);
-                        lines.insert(a / line);
+                        for (int64_t n = 0; n < (all_cols ? ncol : 1); n++) {
+                            const int64_t a = rel[pos[(q * 32 + l) * ncol + n]];
+                            piece.push_back(a / pe);
+                            if (n == 0) lines.insert(a / line);
+                        }
                     }
                     std::sort(piece.begin(), piece.end());
                     for (size_t i = 0; i < piece.size() && ok; i += (size_t)pe)
                         if (piece[i] != piece[i + (size_t)pe - 1] || (i + (size_t)pe < piece.size() && piece[i + (size_t)pe] == piece[i])) ok = false;
-                    if (lines.size() > 4) ok = false;
+                    if (lines.size() > (all_cols ? 16u : 4u)) ok = false;
                 }
                 for (int64_t ml = 0; ml + 1 < TM && pairs; ml += 2) {
                     const int64_t a0 = rel[pos[ml * ncol]], a1 = rel[pos[(ml + 1) * ncol]];

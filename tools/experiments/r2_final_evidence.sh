@@ -32,4 +32,9 @@ cut -c1-300 gpurun_out/r2_bench_reference.json
 # (5) SIMT stem kernel: direct vs staged form on rows-fastest outputs (one process each)
 for v in 1 0 1 0; do TNB_STEM_SIMT_DIRECT=$v timeout 120 python tools/probes/simt_direct_probe.py 2>&1 | tail -1; done > gpurun_out/simt_direct_probe.txt
 cat gpurun_out/simt_direct_probe.txt | cut -c1-600
+# (6) experiment: all-columns direct rule for the SIMT form (TNB_STEM_DIRECT=3) on the skinny MPO step of configs[4]
+for v in 3 2; do
+  TNB_STEM_DIRECT=$v timeout 300 python bench.py --workload mps_mpo --no-cpu --no-extras > gpurun_out/r2_bench_mpo_mode$v.json 2> gpurun_out/r2_bench_mpo_mode$v.err
+  echo "mps_mpo TNB_STEM_DIRECT=$v $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_mpo_mode$v.json'));print(d['value'], d['roofline']['kernels']['stem'])")"
+done
 du -sh gpurun_out
