@@ -7,7 +7,8 @@ import sys
 import numpy as np
 import torch
 
-import tenet_jl_b200 as tb
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import tenet_jl_b200 as tb  # noqa: E402
 
 
 def main():
