@@ -311,7 +311,10 @@ int launch(tnb_ctx* ctx, const StemArgs& a) {
         stem_direct_kernel<E, VM, NMAX, PAIR_><<<(unsigned)grid, threads, dsmem, ctx->stream>>>(a);             \
     } while (0)
     static const int simt_direct = [] { const char* e = getenv("TNB_STEM_SIMT_DIRECT"); return e ? atoi(e) : 1; }();   // 0: staged form only (comparison)
-    if (a.direct && simt_direct) {
+    // direct form only while the accumulators leave room for 3 CTAs per SM (<= 32 registers of them): with N = 16 complex128
+    // it needs 128 registers and measured slower than the staged form (3.20 vs 3.96 TB/s, profiles/r2_simt_direct_probe.txt)
+    const int nmax_ = a.N <= 4 ? 4 : (a.N <= 8 ? 8 : 16);
+    if (a.direct && simt_direct && sizeof(E) / 4 * VM * nmax_ <= 32) {
         const bool pair = VM == 2 && a.pairs && ((uintptr_t)a.C % 16) == 0;
         if (pair) {
             if (a.N <= 4) ST_LAUNCH_DIRECT(4, (VM == 2));
